@@ -1,0 +1,148 @@
+"""The oracle (oracle/fast.py) against the golden vectors produced by the
+verbatim reference (oracle/gen_golden.py).  CPU only."""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import fast
+from conftest import golden
+
+
+def test_reification_matches_reference_bitwise():
+    g = golden("reification.npz")
+    for tag in ("m2", "m3", "m4", "m5", "edge"):
+        mean, var = fast.reification(g[f"y_{tag}"], g[f"s_{tag}"])
+        # same NumPy expressions + same LAPACK => identical bits in this image;
+        # allow a few ulp so a different BLAS build does not fail the oracle test
+        np.testing.assert_allclose(mean, g[f"mean_{tag}"], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(var, g[f"var_{tag}"], rtol=1e-12, atol=0)
+
+
+def test_kg_closed_form_equals_reference_loop():
+    g = golden("kg.npz")
+    for k in range(int(g["ncases"])):
+        mu, var, M = g[f"mu_{k}"], g[f"var_{k}"], int(g[f"M_{k}"])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            nu_star, x_star, nu = fast.kg_diag(mu, var, 0.1, M)
+        assert x_star == int(g[f"x_star_{k}"]), k
+        assert nu_star == float(g[f"nu_star_{k}"]), k
+        ref = g[f"NU_{k}"]
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(nu), fin) or np.array_equal(np.isnan(nu), np.isnan(ref))
+        np.testing.assert_array_equal(nu[fin], ref[fin])
+
+
+def test_elementwise_acquisitions():
+    g = golden("acq.npz")
+    y, std = g["y"], g["std"]
+    for name, fn, args in (("ei", fast.expected_improvement, (float(g["curr_max"]), float(g["xi"]))),
+                           ("pi", fast.probability_improvement, (float(g["curr_max"]), float(g["xi"]))),
+                           ("ucb", fast.upper_conf_bound, (float(g["kt"]),))):
+        mx, idx, allv = fn(*args, y, std)
+        assert idx == int(g[name + "_idx"])
+        assert mx == float(g[name + "_max"])
+        np.testing.assert_array_equal(allv, g[name + "_all"])
+
+
+def test_gp_posterior():
+    g = golden("gp.npz")
+    for k in range(int(g["ncases"])):
+        d = int(g[f"d_{k}"])
+        sn = g[f"sn_{k}"]
+        sn = float(sn) if sn.ndim == 0 else sn
+        gp = fast.GP(g[f"x_{k}"], g[f"y_{k}"], g[f"l_{k}"], float(g[f"sf_{k}"]), sn, d,
+                     str(g[f"kern_{k}"]))
+        mu, var = gp.predict_var(g[f"xs_{k}"])
+        np.testing.assert_allclose(mu, g[f"mu_{k}"], rtol=1e-11, atol=1e-12)
+        np.testing.assert_allclose(var, g[f"var_{k}"], rtol=1e-10, atol=1e-12)
+        if f"cov20_{k}" in g:
+            _, cov = gp.predict_cov(g[f"xs_{k}"][:20])
+            np.testing.assert_allclose(cov, g[f"cov20_{k}"], rtol=1e-10, atol=1e-12)
+
+
+def _model(g, pre):
+    d = int(g[pre + "d"])
+    return fast.ModelReification(
+        [g[pre + f"x_train{i}"] for i in range(3)], [g[pre + f"y_train{i}"] for i in range(3)],
+        g[pre + "model_l"], g[pre + "model_sf"], g[pre + "model_sn"], g[pre + "means"],
+        g[pre + "std"], g[pre + "err_l"], g[pre + "err_sf"], g[pre + "err_sn"],
+        g[pre + "x_true"], g[pre + "y_true"], 3, d, str(g[pre + "kern"]))
+
+
+@pytest.mark.parametrize("cidx", [0, 1, 2])
+def test_tm_stage_work_items(cidx):
+    g = golden("workitems.npz")
+    pre = f"c{cidx}_"
+    model = _model(g, pre)
+    kern = str(g[pre + "kern"])
+    x_fused, x_test, hps = g[pre + "x_fused"], g[pre + "x_test"], g[pre + "hps"]
+    for i in range(3):
+        np.testing.assert_allclose(model.predict_low_order(x_test, i)[0], g[pre + "new_mean"][i],
+                                   rtol=1e-10, atol=1e-12)
+    model.create_fused_GP(x_fused, hps[0, 1:], hps[0, 0], 0.1, kern)
+    mu, var = model.predict_fused_GP(x_test)
+    np.testing.assert_allclose(mu, g[pre + "fused_mu0"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(var, g[pre + "fused_var0"], rtol=1e-9, atol=1e-11)
+    for opt in ("KG", "EI", "PI", "UCB", "Greedy"):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            vals, idxs = fast.fused_calculate_batch(model, x_fused, hps, kern, x_test,
+                                                    float(g[pre + "curr_max"]), opt, iteration=3)
+        np.testing.assert_array_equal(idxs, g[pre + f"tm_{opt}_idx"])
+        np.testing.assert_allclose(vals, g[pre + f"tm_{opt}_val"], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("cidx", [0, 1, 2])
+def test_rom_stage_work_items(cidx):
+    g = golden("workitems.npz")
+    pre = f"c{cidx}_"
+    kern = str(g[pre + "kern"])
+    x_fused, x_test, hps = g[pre + "x_fused"], g[pre + "x_test"], g[pre + "hps"]
+    costs = g[pre + "costs"]
+    new_mean = g[pre + "new_mean"]
+    d = x_test.shape[1]
+    for opt in ("KG", "EI", "PI", "UCB", "Greedy"):
+        ref = g[pre + f"rom_{opt}"]
+        row = 0
+        for jj in range(3):
+            for kk in g[pre + "rom_kks"]:
+                model = _model(g, pre)
+                model.update_GP(x_test[kk][None], np.array([new_mean[jj][kk]]), jj)
+                targets = model.fused_targets(x_fused)
+                for mm in range(hps.shape[0]):
+                    model.create_fused_GP(x_fused, hps[mm, 1:], hps[mm, 0], 0.1, kern, targets)
+                    mu, var = model.predict_fused_GP(x_test)
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        v, i = fast.acquisition(opt, mu, var, float(g[pre + "curr_max"]), d, 3, "ROM")
+                    exp = ref[row]
+                    assert (int(exp[3]), int(exp[4]), int(exp[5])) == (jj, int(kk), mm)
+                    assert i == int(exp[2]), (opt, jj, kk, mm)
+                    np.testing.assert_allclose(np.max(mu), exp[0], rtol=1e-9, atol=1e-12)
+                    scale = 1.0 if opt == "Greedy" else costs[jj]
+                    np.testing.assert_allclose(v / scale, exp[1], rtol=1e-8, atol=1e-12)
+                    row += 1
+
+
+def test_batch_only_work_items():
+    g = golden("batch.npz")
+    d = int(g["d"])
+    for kidx in range(3):
+        pre = f"k{kidx}_"
+        kern = str(g[pre + "kern"])
+        gp = fast.GP(g["x"], g["y"], np.ones(d), 1, 0.05, d, kern)
+        for opt in ("EI", "PI", "UCB", "Greedy"):
+            vals, idxs = fast.batch_acquisition_batch(gp, g["hps"], g["x_test"], float(g["curr_max"]),
+                                                      opt, iteration=2)
+            np.testing.assert_array_equal(idxs, g[pre + f"{opt}_idx"])
+            np.testing.assert_allclose(vals, g[pre + f"{opt}_val"], rtol=1e-9, atol=1e-12)
+
+
+def test_kmedoids_max():
+    g = golden("kmedoids.npz")
+    med3, _ = fast.kmedoids_max(g["X3"], int(g["k3"]))
+    np.testing.assert_array_equal(med3, g["med3"])
+    med2, _ = fast.kmedoids_max(g["X2"], int(g["k2"]))
+    np.testing.assert_array_equal(med2, g["med2"])
