@@ -1,0 +1,215 @@
+// k-medoids primitives behind kmedoids_max (util.py:38-49 -> sklearn_extra KMedoids with the
+// defaults: euclidean, "alternate", "heuristic" init).  The N' x N' distance matrix the
+// reference materialises (80 GB at N' = 1e5) is never formed: distances are recomputed from
+// the N' x f feature rows (f = 2 or 3, barefoot.py:1832,2020,2152) on the FP64 pipe.
+// Distances use the direct form sqrt(sum (x - y)^2).
+#include "bf_common.cuh"
+
+#define KM_THREADS 128
+#define KM_TILE 1024
+#define KM_MAX_F 8
+
+__device__ __forceinline__ double km_dist(const double* __restrict__ a, const double* __restrict__ b, int f) {
+    double s = 0.0;
+    for (int c = 0; c < f; ++c) {
+        const double d = a[c] - b[c];
+        s = fma(d, d, s);
+    }
+    return sqrt(s);
+}
+
+// rowsum[i - row0] = sum_j |x_i - x_j|: one thread per row, all rows staged tile by tile
+template <int F>
+__global__ void __launch_bounds__(KM_THREADS) bf_km_rowsum_kernel(long long N, const double* __restrict__ X,
+                                                                  long long row0, long long rows,
+                                                                  double* __restrict__ rowsum) {
+    constexpr int TILE = (F <= 4) ? KM_TILE : KM_TILE / 2;
+    __shared__ double tile[TILE * F];
+    const long long r = (long long)blockIdx.x * KM_THREADS + threadIdx.x;
+    const bool live = r < rows;
+    double xi[F];
+#pragma unroll
+    for (int c = 0; c < F; ++c) xi[c] = live ? X[(size_t)(row0 + r) * F + c] : 0.0;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long j0 = 0; j0 < N; j0 += TILE) {
+        const int cnt = (int)((N - j0 < TILE) ? (N - j0) : TILE);
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt * F; e += KM_THREADS) tile[e] = X[(size_t)j0 * F + e];
+        __syncthreads();
+        int j = 0;
+        for (; j + 4 <= cnt; j += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                double s = 0.0;
+#pragma unroll
+                for (int c = 0; c < F; ++c) {
+                    const double d = xi[c] - tile[(j + u) * F + c];
+                    s = fma(d, d, s);
+                }
+                acc[u] += sqrt(s);
+            }
+        }
+        for (; j < cnt; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < F; ++c) {
+                const double d = xi[c] - tile[j * F + c];
+                s = fma(d, d, s);
+            }
+            acc[0] += sqrt(s);
+        }
+    }
+    if (live) rowsum[r] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
+extern "C" int bf_kmedoids_rowsum(long long N, int f, const double* X, long long row0, long long rows,
+                                  double* rowsum, void* stream) {
+    BF_CHECK_ARG(N > 0 && X && rowsum && row0 >= 0 && rows >= 0 && row0 + rows <= N, BF_ERR_ARG,
+                 "bf_kmedoids_rowsum: bad argument");
+    BF_CHECK_ARG(f >= 1 && f <= KM_MAX_F, BF_ERR_SIZE, "bf_kmedoids_rowsum: f=%d outside 1..%d", f, KM_MAX_F);
+    if (rows == 0) return 0;
+    const unsigned grid = (unsigned)((rows + KM_THREADS - 1) / KM_THREADS);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (f) {
+#define BF_CASE(FF) case FF: bf_km_rowsum_kernel<FF><<<grid, KM_THREADS, 0, st>>>(N, X, row0, rows, rowsum); break;
+        BF_CASE(1) BF_CASE(2) BF_CASE(3) BF_CASE(4) BF_CASE(5) BF_CASE(6) BF_CASE(7) BF_CASE(8)
+#undef BF_CASE
+    }
+    BF_CHECK_LAUNCH("bf_kmedoids_rowsum");
+    return 0;
+}
+
+// labels[i] = first argmin over the medoids (np.argmin(D[medoids, :], axis=0))
+__global__ void __launch_bounds__(KM_THREADS) bf_km_assign_kernel(long long N, int f, int k,
+                                                                  const double* __restrict__ X,
+                                                                  const long long* __restrict__ medoid_idx,
+                                                                  int32_t* __restrict__ labels) {
+    extern __shared__ double med[];   // k * f
+    for (int e = threadIdx.x; e < k * f; e += KM_THREADS) {
+        const int c = e / f, a = e - c * f;
+        med[e] = X[(size_t)medoid_idx[c] * f + a];
+    }
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * KM_THREADS + threadIdx.x;
+    if (i >= N) return;
+    double xi[KM_MAX_F];
+    for (int a = 0; a < f; ++a) xi[a] = X[(size_t)i * f + a];
+    double best = INFINITY;
+    int lab = 0;
+    for (int c = 0; c < k; ++c) {
+        const double d = km_dist(xi, med + c * f, f);
+        if (d < best) {
+            best = d;
+            lab = c;
+        }
+    }
+    labels[i] = lab;
+}
+
+extern "C" int bf_kmedoids_assign(long long N, int f, int k, const double* X, const long long* medoid_idx,
+                                  int32_t* labels, void* stream) {
+    BF_CHECK_ARG(N > 0 && k > 0 && X && medoid_idx && labels, BF_ERR_ARG, "bf_kmedoids_assign: bad argument");
+    BF_CHECK_ARG(f >= 1 && f <= KM_MAX_F, BF_ERR_SIZE, "bf_kmedoids_assign: f=%d outside 1..%d", f, KM_MAX_F);
+    BF_CHECK_ARG((size_t)k * f * sizeof(double) <= 48 * 1024, BF_ERR_SIZE, "bf_kmedoids_assign: k*f too large");
+    const unsigned grid = (unsigned)((N + KM_THREADS - 1) / KM_THREADS);
+    bf_km_assign_kernel<<<grid, KM_THREADS, (size_t)k * f * sizeof(double), (cudaStream_t)stream>>>(
+        N, f, k, X, medoid_idx, labels);
+    BF_CHECK_LAUNCH("bf_kmedoids_assign");
+    return 0;
+}
+
+// cost[p] = sum over the segment of p of |x_perm[p] - x_perm[q]|, q in segment order
+__global__ void __launch_bounds__(KM_THREADS) bf_km_cost_kernel(long long N, int f, int k,
+                                                                const double* __restrict__ X,
+                                                                const long long* __restrict__ perm,
+                                                                const long long* __restrict__ seg,
+                                                                double* __restrict__ cost) {
+    const long long p = (long long)blockIdx.x * KM_THREADS + threadIdx.x;
+    if (p >= N) return;
+    int lo = 0, hi = k;           // segment c with seg[c] <= p < seg[c + 1]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (seg[mid] <= p) lo = mid; else hi = mid;
+    }
+    const long long q0 = seg[lo], q1 = seg[lo + 1];
+    double xi[KM_MAX_F];
+    const long long me = perm[p];
+    for (int a = 0; a < f; ++a) xi[a] = X[(size_t)me * f + a];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    long long q = q0;
+    for (; q + 4 <= q1; q += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] += km_dist(xi, X + (size_t)perm[q + u] * f, f);
+    }
+    for (; q < q1; ++q) acc[0] += km_dist(xi, X + (size_t)perm[q] * f, f);
+    cost[p] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
+extern "C" int bf_kmedoids_cluster_cost(long long N, int f, int k, const double* X, const long long* perm,
+                                        const long long* seg, double* cost, void* stream) {
+    BF_CHECK_ARG(N > 0 && k > 0 && X && perm && seg && cost, BF_ERR_ARG, "bf_kmedoids_cluster_cost: bad argument");
+    BF_CHECK_ARG(f >= 1 && f <= KM_MAX_F, BF_ERR_SIZE, "bf_kmedoids_cluster_cost: f=%d outside 1..%d", f, KM_MAX_F);
+    const unsigned grid = (unsigned)((N + KM_THREADS - 1) / KM_THREADS);
+    bf_km_cost_kernel<<<grid, KM_THREADS, 0, (cudaStream_t)stream>>>(N, f, k, X, perm, seg, cost);
+    BF_CHECK_LAUNCH("bf_kmedoids_cluster_cost");
+    return 0;
+}
+
+// one CTA per cluster: first argmin of the in-cluster costs; move the medoid only if strictly
+// better than the current one (sklearn_extra _update_medoid_idxs_in_place)
+__global__ void __launch_bounds__(256) bf_km_update_kernel(const long long* __restrict__ perm,
+                                                           const long long* __restrict__ seg,
+                                                           const double* __restrict__ cost,
+                                                           long long* __restrict__ medoid_idx,
+                                                           int32_t* __restrict__ changed) {
+    const int c = blockIdx.x;
+    const long long q0 = seg[c], q1 = seg[c + 1];
+    if (q1 <= q0) return;         // empty cluster: medoid kept
+    const long long cur = medoid_idx[c];
+    double bv = INFINITY;
+    long long bp = 0x7fffffffffffffffLL;
+    long long curp = 0x7fffffffffffffffLL;
+    for (long long q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+        const double v = cost[q];
+        if (v < bv || (v == bv && q < bp)) {
+            bv = v;
+            bp = q;
+        }
+        if (perm[q] == cur && q < curp) curp = q;
+    }
+    __shared__ double sv[256];
+    __shared__ long long sp[256], sc[256];
+    sv[threadIdx.x] = bv;
+    sp[threadIdx.x] = bp;
+    sc[threadIdx.x] = curp;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            const double v = sv[threadIdx.x + s];
+            const long long q = sp[threadIdx.x + s];
+            if (v < sv[threadIdx.x] || (v == sv[threadIdx.x] && q < sp[threadIdx.x])) {
+                sv[threadIdx.x] = v;
+                sp[threadIdx.x] = q;
+            }
+            if (sc[threadIdx.x + s] < sc[threadIdx.x]) sc[threadIdx.x] = sc[threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        // np.argmax(cluster_idxs == medoid) is 0 when the medoid is not in its own cluster
+        const long long cp = (sc[0] == 0x7fffffffffffffffLL) ? q0 : sc[0];
+        if (sv[0] < cost[cp]) {
+            medoid_idx[c] = perm[sp[0]];
+            atomicAdd(changed, 1);
+        }
+    }
+}
+
+extern "C" int bf_kmedoids_update(long long N, int k, const long long* perm, const long long* seg,
+                                  const double* cost, long long* medoid_idx, int32_t* changed, void* stream) {
+    BF_CHECK_ARG(N > 0 && k > 0 && perm && seg && cost && medoid_idx && changed, BF_ERR_ARG,
+                 "bf_kmedoids_update: bad argument");
+    bf_km_update_kernel<<<k, 256, 0, (cudaStream_t)stream>>>(perm, seg, cost, medoid_idx, changed);
+    BF_CHECK_LAUNCH("bf_kmedoids_update");
+    return 0;
+}

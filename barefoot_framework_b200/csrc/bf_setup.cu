@@ -1,0 +1,338 @@
+// Per-set GP setup on the device: kernel matrix, batched Cholesky, L^-1 (+ tensor-core operand
+// packing) and alpha.  Replaces gp_model.create_kernel/create_gp (gpModel.py:29-42), i.e.
+// george GP.compute -> scipy cholesky, and the cho_solve for alpha behind gpModel.py:47,53.
+// All matrices are np x np row-major, np = n rounded up to 32, padded with the identity so
+// every 32 x 32 block is full.
+#include "bf_common.cuh"
+
+// ---- K = amp k(X, X) + diag(yerr_eff^2) ------------------------------------------------------
+__global__ void __launch_bounds__(256) bf_kernel_matrix_kernel(
+    int kern, int n, int d, int np, const double* __restrict__ X, const double* __restrict__ inv_l2,
+    const double* __restrict__ amp, const int32_t* __restrict__ set_hp, const double* __restrict__ yerr,
+    int yerr_n, long long yerr_stride, double* __restrict__ K) {
+    __shared__ double xi_s[32][BF_MAX_DIM + 1];
+    __shared__ double xj_s[32][BF_MAX_DIM + 1];
+    __shared__ double w_s[BF_MAX_DIM];
+    const int set = blockIdx.z;
+    const int hp = set_hp ? set_hp[set] : set;
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < 32 * d; e += 256) {
+        const int r = e / d, a = e - r * d;
+        xi_s[r][a] = (i0 + r < n) ? X[(size_t)(i0 + r) * d + a] : 0.0;
+        xj_s[r][a] = (j0 + r < n) ? X[(size_t)(j0 + r) * d + a] : 0.0;
+    }
+    if (threadIdx.x < d) w_s[threadIdx.x] = inv_l2[(size_t)hp * d + threadIdx.x];
+    __syncthreads();
+    const double am = amp[hp];
+    double* Kset = K + (size_t)set * np * np;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const int r = ty + 8 * rr;
+        const int i = i0 + r, j = j0 + tx;
+        double v;
+        if (i < n && j < n) {
+            double r2 = 0.0;
+            for (int a = 0; a < d; ++a) {
+                const double df = xi_s[r][a] - xj_s[tx][a];
+                r2 = fma(df * df, w_s[a], r2);
+            }
+            v = am * bf_radial(kern, r2);
+            if (i == j) {
+                const double e = yerr_n == 1 ? yerr[0] : yerr[(size_t)set * yerr_stride + i];
+                const double s = sqrt(e * e + BF_TINY);   // george folds the jitter into yerr
+                v += s * s;
+            }
+        } else {
+            v = (i == j) ? 1.0 : 0.0;
+        }
+        Kset[(size_t)i * np + j] = v;
+    }
+}
+
+extern "C" int bf_kernel_matrix(int kern, int n, int d, int S, const double* X, const double* inv_l2,
+                                const double* amp, const int32_t* set_hp, const double* yerr,
+                                int yerr_n, long long yerr_stride, double* K, void* stream) {
+    BF_CHECK_ARG(kern >= BF_KERN_SE && kern <= BF_KERN_M52, BF_ERR_ARG, "bf_kernel_matrix: bad kern %d", kern);
+    BF_CHECK_ARG(n > 0 && S >= 0 && X && inv_l2 && amp && yerr && K, BF_ERR_ARG, "bf_kernel_matrix: bad argument");
+    BF_CHECK_ARG(d >= 1 && d <= BF_MAX_DIM, BF_ERR_SIZE, "bf_kernel_matrix: nDim %d outside 1..%d", d, BF_MAX_DIM);
+    BF_CHECK_ARG(yerr_n == 1 || yerr_n == n, BF_ERR_ARG, "bf_kernel_matrix: yerr_n must be 1 or n");
+    BF_CHECK_ARG(S <= 65535, BF_ERR_SIZE, "bf_kernel_matrix: at most 65535 sets per call");
+    if (S == 0) return 0;
+    const int np = bf_padded_n(n);
+    dim3 grid(np / 32, np / 32, S);
+    bf_kernel_matrix_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(kern, n, d, np, X, inv_l2, amp, set_hp,
+                                                                    yerr, yerr_n, yerr_stride, K);
+    BF_CHECK_LAUNCH("bf_kernel_matrix");
+    return 0;
+}
+
+// ---- 32 x 32 tile product on the tensor cores -------------------------------------------------
+// c[4][4][2] += Arows(32 x 4k) * Brows(32 x 4k)^T for k-steps [0, ksteps): both operands are
+// row-major with leading dimension ld, fragment element (row = lane >> 2, col = lane & 3).
+__device__ __forceinline__ void bf_tile_abt(double (&c)[4][4][2], const double* __restrict__ Arow,
+                                            const double* __restrict__ Brow, int ld, int ksteps) {
+    const int lane = threadIdx.x & 31;
+    const double* ap = Arow + (size_t)(lane >> 2) * ld + (lane & 3);
+    const double* bp = Brow + (size_t)(lane >> 2) * ld + (lane & 3);
+    for (int ks = 0; ks < ksteps; ++ks) {
+        double a[4], b[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            a[t] = ap[(size_t)(8 * t) * ld + 4 * ks];
+            b[t] = bp[(size_t)(8 * t) * ld + 4 * ks];
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) bf_dmma(c[t][u][0], c[t][u][1], a[t], b[u]);
+    }
+}
+
+// ---- batched Cholesky (left-looking, 32-wide panels, one CTA per matrix) ----------------------
+__global__ void __launch_bounds__(BF_THREADS) bf_cholesky_kernel(int n, int np, double* __restrict__ Aall,
+                                                                 int32_t* __restrict__ info) {
+    __shared__ double Ld[32][33];
+    __shared__ int bad;
+    double* A = Aall + (size_t)blockIdx.x * np * np;
+    const int nb = np / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    for (int kb = 0; kb < nb; ++kb) {
+        const int r0 = 32 * kb;
+        // 1. panel update with the columns already factored: P -= A[:, :r0] A[r0:r0+32, :r0]^T
+        if (kb > 0) {
+            for (int rb = kb + warp; rb < nb; rb += BF_WARPS) {
+                double c[4][4][2];
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) c[t][u][0] = c[t][u][1] = 0.0;
+                bf_tile_abt(c, A + (size_t)(32 * rb) * np, A + (size_t)r0 * np, np, r0 / 4);
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        double2* dst = reinterpret_cast<double2*>(
+                            A + (size_t)(32 * rb + 8 * t + (lane >> 2)) * np + r0 + 8 * u + 2 * (lane & 3));
+                        double2 v = *dst;
+                        v.x -= c[t][u][0];
+                        v.y -= c[t][u][1];
+                        *dst = v;
+                    }
+            }
+        }
+        __syncthreads();
+        // 2. factor the diagonal block (warp 0, lane = row)
+        if (warp == 0) {
+            for (int j = 0; j < 32; ++j) Ld[lane][j] = A[(size_t)(r0 + lane) * np + r0 + j];
+            __syncwarp();
+            for (int j = 0; j < 32; ++j) {
+                const double djj = Ld[j][j];
+                if (!(djj > 0.0) && lane == 0 && bad == 0) bad = r0 + j + 1;
+                const double dj = sqrt(djj);
+                __syncwarp();
+                if (lane == j) Ld[j][j] = dj;
+                if (lane > j) Ld[lane][j] = Ld[lane][j] / dj;
+                __syncwarp();
+                if (lane > j) {
+                    const double lij = Ld[lane][j];
+                    for (int cc = j + 1; cc <= lane; ++cc) Ld[lane][cc] = fma(-lij, Ld[cc][j], Ld[lane][cc]);
+                }
+                __syncwarp();
+            }
+            for (int j = 0; j < 32; ++j) A[(size_t)(r0 + lane) * np + r0 + j] = (j <= lane) ? Ld[lane][j] : 0.0;
+        }
+        __syncthreads();
+        // 3. rows below the block: X L_kk^T = P, one row per thread
+        for (int i = r0 + 32 + threadIdx.x; i < np; i += BF_THREADS) {
+            double x[32];
+            double* row = A + (size_t)i * np + r0;
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) x[cc] = row[cc];
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) {
+                double s = x[cc];
+#pragma unroll
+                for (int t = 0; t < cc; ++t) s = fma(-x[t], Ld[cc][t], s);
+                x[cc] = s / Ld[cc][cc];
+            }
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) row[cc] = x[cc];
+        }
+        __syncthreads();
+    }
+    // the strictly upper 32 x 32 blocks still hold K: clear them so the output is L
+    for (int e = threadIdx.x; e < np * (np / 2); e += BF_THREADS) {
+        const int i = e / (np / 2), j2 = (e - i * (np / 2)) * 2;
+        if ((j2 >> 5) > (i >> 5)) *reinterpret_cast<double2*>(A + (size_t)i * np + j2) = make_double2(0.0, 0.0);
+    }
+    if (threadIdx.x == 0 && info) info[blockIdx.x] = bad;
+}
+
+extern "C" int bf_cholesky_batched(int n, int S, double* K_inout_L, int32_t* info, void* stream) {
+    BF_CHECK_ARG(n > 0 && S >= 0 && K_inout_L, BF_ERR_ARG, "bf_cholesky_batched: bad argument");
+    if (S == 0) return 0;
+    const int np = bf_padded_n(n);
+    bf_cholesky_kernel<<<S, BF_THREADS, 0, (cudaStream_t)stream>>>(n, np, K_inout_L, info);
+    BF_CHECK_LAUNCH("bf_cholesky_batched");
+    return 0;
+}
+
+// ---- L^-1, packing, alpha --------------------------------------------------------------------
+__global__ void __launch_bounds__(BF_THREADS) bf_factor_finish_kernel(
+    int n, int np, const double* __restrict__ Lall, const double* __restrict__ y, long long y_stride,
+    double* __restrict__ Linv_all, double* __restrict__ packed_all, size_t packed_stride,
+    double* __restrict__ alpha_all) {
+    extern __shared__ __align__(16) double sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* buf = sm + (size_t)warp * 32 * 33;           // per-warp 32 x 33 scratch
+    double* tvec = sm + (size_t)BF_WARPS * 32 * 33;      // np doubles
+    const int set = blockIdx.x;
+    const double* L = Lall + (size_t)set * np * np;
+    double* Linv = Linv_all + (size_t)set * np * np;
+    double* packed = packed_all + (size_t)set * packed_stride;
+    const int nb = np / 32;
+
+    // phase 1: inverses of the diagonal blocks (lane = column of the inverse)
+    for (int kb = warp; kb < nb; kb += BF_WARPS) {
+        const int r0 = 32 * kb;
+        for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = L[(size_t)(r0 + lane) * np + r0 + j];
+        __syncwarp();
+        double x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            double s = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int t = 0; t < i; ++t) s = fma(-buf[i * 33 + t], x[t], s);   // x[t] = 0 for t < lane
+            x[i] = (i >= lane) ? s / buf[i * 33 + i] : 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            Linv[(size_t)(r0 + i) * np + r0 + lane] = x[i];
+            packed[bf_linv_elem_off(r0 + i, r0 + lane)] = x[i];
+        }
+        // zero the blocks to the right of the diagonal in the row-major copy
+        for (int jb = kb + 1; jb < nb; ++jb)
+            for (int i = 0; i < 32; ++i) Linv[(size_t)(r0 + i) * np + 32 * jb + lane] = 0.0;
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // phase 2: block column J of the inverse, top to bottom; columns are independent, paired
+    // (J, nb-1-J) per warp for balance.  Linv_IJ = -Linv_II * sum_{K=J}^{I-1} L_IK Linv_KJ.
+    const int npairs = (nb + 1) >> 1;
+    for (int pr = warp; pr < npairs; pr += BF_WARPS) {
+        for (int side = 0; side < 2; ++side) {
+            const int J = side == 0 ? pr : nb - 1 - pr;
+            if (side == 1 && J == pr) break;
+            for (int I = J + 1; I < nb; ++I) {
+                double c[4][4][2];
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) c[t][u][0] = c[t][u][1] = 0.0;
+                // T = L[I, J..I-1] * Linv[J..I-1, J]  (B operand is NOT transposed here)
+                {
+                    const double* ap = L + (size_t)(32 * I + (lane >> 2)) * np + 32 * J + (lane & 3);
+                    const double* bp = Linv + (size_t)(32 * J + (lane & 3)) * np + 32 * J + (lane >> 2);
+                    const int ksteps = 8 * (I - J);
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        double a[4], b[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            a[t] = ap[(size_t)(8 * t) * np + 4 * ks];
+                            b[t] = bp[(size_t)(4 * ks) * np + 8 * t];
+                        }
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) bf_dmma(c[t][u][0], c[t][u][1], a[t], b[u]);
+                    }
+                }
+                // stage T in shared memory (row-major 32 x 33) to use it as the next B operand
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = 8 * t + (lane >> 2), cc = 8 * u + 2 * (lane & 3);
+                        buf[r * 33 + cc] = c[t][u][0];
+                        buf[r * 33 + cc + 1] = c[t][u][1];
+                        c[t][u][0] = c[t][u][1] = 0.0;
+                    }
+                __syncwarp();
+                {
+                    const double* ap = Linv + (size_t)(32 * I + (lane >> 2)) * np + 32 * I + (lane & 3);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        double a[4], b[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            a[t] = ap[(size_t)(8 * t) * np + 4 * ks];
+                            b[t] = buf[(4 * ks + (lane & 3)) * 33 + 8 * t + (lane >> 2)];
+                        }
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) bf_dmma(c[t][u][0], c[t][u][1], a[t], b[u]);
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = 32 * I + 8 * t + (lane >> 2), j = 32 * J + 8 * u + 2 * (lane & 3);
+                        double2 v;
+                        v.x = -c[t][u][0];
+                        v.y = -c[t][u][1];
+                        *reinterpret_cast<double2*>(Linv + (size_t)i * np + j) = v;
+                        packed[bf_linv_elem_off(i, j)] = v.x;
+                        packed[bf_linv_elem_off(i, j + 1)] = v.y;
+                    }
+                __syncwarp();
+                __threadfence_block();
+            }
+        }
+    }
+    __syncthreads();
+
+    // phase 3: alpha = Linv^T (Linv y)
+    if (alpha_all) {
+        const double* yv = y + (size_t)set * y_stride;
+        for (int i = threadIdx.x; i < np; i += BF_THREADS) {
+            double s = 0.0;
+            if (i < n) {
+                const double* row = Linv + (size_t)i * np;
+                for (int j = 0; j <= i; ++j) s = fma(row[j], yv[j], s);
+            }
+            tvec[i] = s;
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < n; j += BF_THREADS) {
+            double s = 0.0;
+            for (int i = j; i < n; ++i) s = fma(Linv[(size_t)i * np + j], tvec[i], s);
+            alpha_all[(size_t)set * n + j] = s;
+        }
+    }
+}
+
+extern "C" int bf_factor_finish(int n, int S, const double* L, const double* y, long long y_stride,
+                                double* Linv, double* linv_packed, double* alpha, void* stream) {
+    BF_CHECK_ARG(n > 0 && S >= 0 && L && Linv && linv_packed, BF_ERR_ARG, "bf_factor_finish: bad argument");
+    BF_CHECK_ARG(!alpha || y, BF_ERR_ARG, "bf_factor_finish: alpha requested without y");
+    if (S == 0) return 0;
+    const int np = bf_padded_n(n);
+    const size_t smem = sizeof(double) * ((size_t)BF_WARPS * 32 * 33 + np);
+    cudaError_t e = cudaFuncSetAttribute(bf_factor_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        bf_set_error("bf_factor_finish: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    bf_factor_finish_kernel<<<S, BF_THREADS, smem, (cudaStream_t)stream>>>(
+        n, np, L, y, y_stride, Linv, linv_packed, bf_linv_packed_doubles(n), alpha);
+    BF_CHECK_LAUNCH("bf_factor_finish");
+    return 0;
+}

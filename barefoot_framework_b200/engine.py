@@ -1,0 +1,292 @@
+"""Device pipeline behind the reference-named host classes: batched GP setup,
+posterior + acquisition sweeps, knowledge gradient, reification and k-medoids,
+all through the C ABI in include/barefoot_sm100.h.
+
+One call here covers what the reference fans out as H (or m*N*H) Python work
+items (barefoot.py:1070-1073, 1271-1283, 2001-2013).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (ACQ_EI, ACQ_GREEDY, ACQ_PI, ACQ_UCB, KERN, NSLOT_IDX, NSLOT_VAL, SLOT_EI,
+                   SLOT_GREEDY, SLOT_PI, SLOT_TOP2, SLOT_UCB, call, ptr, stream)
+
+F64 = torch.float64
+SN_KG = 0.1      # util.py:260,619
+XI = 0.01
+
+ACQ_BITS = {"EI": ACQ_EI, "PI": ACQ_PI, "UCB": ACQ_UCB, "Greedy": ACQ_GREEDY, "KG": ACQ_GREEDY}
+ACQ_SLOT = {"EI": SLOT_EI, "PI": SLOT_PI, "UCB": SLOT_UCB, "Greedy": SLOT_GREEDY}
+
+
+def device():
+    _lib.require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_dev(a, dtype=F64):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device(), dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device())
+
+
+def amplitude(sigma_f, ndim):
+    """george: ``c * kernel`` -> ConstantKernel(log(c / ndim)) (oracle/george_shim.py)."""
+    return np.asarray(sigma_f, dtype=np.float64) / ndim
+
+
+def inv_metric(l_sq):
+    """george keeps log(metric) and evaluates exp(-log M)."""
+    return np.exp(-np.log(np.asarray(l_sq, dtype=np.float64)))
+
+
+def ucb_kt(ndim, iteration):
+    """util.py:515-517,607-608."""
+    beta = np.abs((2 * np.log(ndim * (iteration ** 2) * (np.pi ** 2) / (6 / 0.1))) / 5)
+    return float(np.sqrt(0.2 * beta))
+
+
+class GPFactors:
+    """Factorised GPs sharing the training inputs X: one "set" per hyper-parameter
+    set (and, in the ROM stage, per fantasy point)."""
+
+    def __init__(self, kern, X, inv_l2, amp, set_hp, linv_packed, alpha, S, L=None, Linv=None):
+        self.kern, self.X, self.inv_l2, self.amp, self.set_hp = kern, X, inv_l2, amp, set_hp
+        self.linv_packed, self.alpha, self.S = linv_packed, alpha, S
+        self.n, self.d = X.shape
+        self.L, self.Linv = L, Linv
+
+
+def build_factors(kern, X, y, l_sq, sigma_f, yerr, ndim=None, set_hp=None, n_sets=None,
+                  chunk_bytes=2 << 30, keep_dense=False, check=True):
+    """gp_model.__init__ for a batch of sets (gpModel.py:17-42).
+
+    X [n, d]; l_sq [H, d] (already squared where the reference squares, gpModel.py:20);
+    sigma_f [H]; y [n] shared or [S, n]; yerr scalar, [n] shared or [S, n].
+    set_hp [S] maps sets to rows of (l_sq, sigma_f); default identity with S = H."""
+    dev = device()
+    X = to_dev(X).reshape(len(X), -1)
+    n, d = X.shape
+    ndim = d if ndim is None else ndim
+    l_sq = np.atleast_2d(np.asarray(l_sq, dtype=np.float64))
+    H = l_sq.shape[0]
+    inv_l2 = to_dev(inv_metric(l_sq))
+    amp = to_dev(np.atleast_1d(amplitude(sigma_f, ndim)))
+    if set_hp is None and n_sets is not None and n_sets != H:
+        assert H == 1, "n_sets without set_hp needs a single hyper-parameter row"
+        set_hp = np.zeros(n_sets, dtype=np.int32)
+    if set_hp is None:
+        S = H
+        hp_t = None
+    else:
+        hp_t = to_dev(set_hp, torch.int32)
+        S = hp_t.numel()
+    y = to_dev(y)
+    y_stride = n if y.dim() == 2 else 0
+    yerr_t = to_dev(np.atleast_1d(yerr) if not isinstance(yerr, torch.Tensor) else yerr)
+    if yerr_t.dim() == 2:
+        yerr_n, yerr_stride = n, n
+    else:
+        yerr_n, yerr_stride = yerr_t.numel(), 0
+    assert yerr_n in (1, n)
+    lib = _lib.load()
+    np_ = lib.bf_padded_n(n)
+    pdoubles = lib.bf_linv_packed_doubles(n)
+    linv_packed = torch.empty((S, pdoubles), dtype=F64, device=dev)
+    alpha = torch.empty((S, n), dtype=F64, device=dev)
+    info = torch.zeros((S,), dtype=torch.int32, device=dev)
+    per_set = 2 * np_ * np_ * 8
+    chunk = S if keep_dense else max(1, min(S, 65535, chunk_bytes // per_set))
+    Lbuf = torch.empty((chunk, np_, np_), dtype=F64, device=dev)
+    Libuf = torch.empty((chunk, np_, np_), dtype=F64, device=dev)
+    st = stream()
+    for s0 in range(0, S, chunk):
+        sc = min(chunk, S - s0)
+        hp_p = None if hp_t is None else hp_t[s0:].data_ptr()
+        inv_p, amp_p = inv_l2, amp
+        if hp_t is None:    # identity map: shift the HP rows instead
+            inv_p, amp_p = inv_l2[s0:], amp[s0:]
+        call("bf_kernel_matrix", KERN[kern], n, d, sc, ptr(X), inv_p.data_ptr(), amp_p.data_ptr(), hp_p,
+             yerr_t[s0:].data_ptr() if yerr_stride else ptr(yerr_t), yerr_n, yerr_stride, ptr(Lbuf), st)
+        call("bf_cholesky_batched", n, sc, ptr(Lbuf), info[s0:].data_ptr(), st)
+        call("bf_factor_finish", n, sc, ptr(Lbuf), y[s0:].data_ptr() if y_stride else ptr(y), y_stride,
+             ptr(Libuf), linv_packed[s0:].data_ptr(), alpha[s0:].data_ptr(), st)
+    bad = int(info.max().item()) if (S and check) else 0
+    if bad:
+        raise np.linalg.LinAlgError("%d-th leading minor of a GP kernel matrix is not positive definite" % bad)
+    return GPFactors(kern, X, inv_l2, amp, hp_t, linv_packed, alpha, S,
+                     L=Lbuf if keep_dense else None, Linv=Libuf if keep_dense else None)
+
+
+class SweepResult:
+    def __init__(self):
+        self.mu = self.var = self.best_val = self.best_idx = None
+
+
+# bench.py sets this to a list to receive one (start, end) CUDA-event pair per bf_gp_posterior launch
+posterior_events = None
+
+
+def posterior_sweep(f, Xs, scale=None, shift=None, want_mu=False, want_var=False, acq_mask=0,
+                    spread_is_sqrt=False, curr_max=0.0, xi=XI, kt=0.0):
+    """gp_model.predict_var (gpModel.py:50-54) for every set of `f` at the candidates
+    Xs [N, d], with the de-normalisation of predict_fused_GP / predict_low_order
+    (reificationFusion.py:189-206) and the elementwise acquisitions fused in."""
+    dev = device()
+    Xs = to_dev(Xs).reshape(len(Xs), -1)
+    N = Xs.shape[0]
+    assert Xs.shape[1] == f.d
+    lib = _lib.load()
+    out = SweepResult()
+    S = f.S
+    if want_mu:
+        out.mu = torch.empty((S, N), dtype=F64, device=dev)
+    if want_var:
+        out.var = torch.empty((S, N), dtype=F64, device=dev)
+    tiles = lib.bf_posterior_tiles(f.n, N)
+    pv = pi = None
+    if acq_mask:
+        pv = torch.empty((S, tiles, NSLOT_VAL), dtype=F64, device=dev)
+        pi = torch.empty((S, tiles, NSLOT_IDX), dtype=torch.int64, device=dev)
+        out.best_val = torch.empty((S, NSLOT_VAL), dtype=F64, device=dev)
+        out.best_idx = torch.empty((S, NSLOT_IDX), dtype=torch.int64, device=dev)
+    st = stream()
+    for s0 in range(0, S, 65535):
+        sc = min(65535, S - s0)
+        sl = slice(s0, s0 + sc)
+        hp_p = None if f.set_hp is None else f.set_hp[s0:].data_ptr()
+        inv_p = f.inv_l2 if f.set_hp is not None else f.inv_l2[s0:]
+        amp_p = f.amp if f.set_hp is not None else f.amp[s0:]
+        if posterior_events is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        call("bf_gp_posterior", KERN[f.kern], N, f.n, f.d, sc, ptr(Xs), ptr(f.X), inv_p.data_ptr(),
+             amp_p.data_ptr(), hp_p, f.linv_packed[s0:].data_ptr(), f.alpha[s0:].data_ptr(),
+             None if scale is None else scale[s0:].data_ptr(),
+             None if shift is None else shift[s0:].data_ptr(),
+             None if out.mu is None else out.mu[s0:].data_ptr(),
+             None if out.var is None else out.var[s0:].data_ptr(),
+             acq_mask, int(bool(spread_is_sqrt)), float(curr_max), float(xi), float(kt),
+             None if pv is None else pv[sl].data_ptr(), None if pi is None else pi[sl].data_ptr(), st)
+        if posterior_events is not None:
+            ev1.record()
+            posterior_events.append((ev0, ev1))
+        if acq_mask:
+            call("bf_acq_finalize", sc, tiles, acq_mask, pv[sl].data_ptr(), pi[sl].data_ptr(),
+                 out.best_val[sl].data_ptr(), out.best_idx[sl].data_ptr(), st)
+    return out
+
+
+def kg_from_sweep(res, M=None, sn=SN_KG, want_nu=False):
+    """knowledge_gradient on np.diag(var) (acquisitionFunc.py:12-96 via util.py:259-262):
+    needs a sweep run with want_mu, want_var and ACQ_GREEDY."""
+    dev = device()
+    S, N = res.mu.shape
+    M = N if M is None else M
+    lib = _lib.load()
+    tiles = lib.bf_kg_tiles(N)
+    pv = torch.empty((S, tiles), dtype=F64, device=dev)
+    pi = torch.empty((S, tiles), dtype=torch.int64, device=dev)
+    kg_val = torch.empty((S,), dtype=F64, device=dev)
+    kg_idx = torch.empty((S,), dtype=torch.int64, device=dev)
+    nu = torch.full((S, N), float("-inf"), dtype=F64, device=dev) if want_nu else None
+    st = stream()
+    for s0 in range(0, S, 65535):
+        sc = min(65535, S - s0)
+        call("bf_kg_diag", N, M, sc, res.mu[s0:].data_ptr(), res.var[s0:].data_ptr(),
+             res.best_val[s0:].data_ptr(), res.best_idx[s0:].data_ptr(), float(sn),
+             None if nu is None else nu[s0:].data_ptr(), pv[s0:].data_ptr(), pi[s0:].data_ptr(),
+             kg_val[s0:].data_ptr(), kg_idx[s0:].data_ptr(), st)
+    return kg_val, kg_idx, nu
+
+
+def acquisition_sweep(f, Xs, name, stage, curr_max, iteration, scale=None, shift=None, xi=XI, M=None):
+    """One acquisition for every set: returns device tensors (values [S], indices [S]).
+    stage "ROM": PI/UCB see sqrt(var) (util.py:451,519); "TM"/"BATCH": var (util.py:598-612)."""
+    kt = ucb_kt(f.d, iteration) if name == "UCB" else 0.0
+    kg = name == "KG"
+    res = posterior_sweep(f, Xs, scale, shift, want_mu=kg, want_var=kg, acq_mask=ACQ_BITS[name],
+                          spread_is_sqrt=(stage == "ROM"), curr_max=curr_max, xi=xi, kt=kt)
+    if kg:
+        v, i, _ = kg_from_sweep(res, M=M)
+        return v, i, res
+    slot = ACQ_SLOT[name]
+    return res.best_val[:, slot], res.best_idx[:, slot], res
+
+
+def reification(y, var):
+    """reification(y, sig) (reificationFusion.py:26-57) on device tensors [m, P]."""
+    y = to_dev(y)
+    var = to_dev(var)
+    m, P = y.shape
+    mean_f = torch.empty((P,), dtype=F64, device=y.device)
+    var_f = torch.empty((P,), dtype=F64, device=y.device)
+    call("bf_reification", m, P, ptr(y), ptr(var), ptr(mean_f), ptr(var_f), stream())
+    return mean_f, var_f
+
+
+def affine(a, scale, shift):
+    out = torch.empty_like(a)
+    call("bf_affine", a.numel(), ptr(a), float(scale), float(shift), ptr(out), stream())
+    return out
+
+
+def total_variance(err_mu, err_std, err_mean, var, model_std):
+    out = torch.empty_like(var)
+    call("bf_total_variance", var.numel(), ptr(err_mu), float(err_std), float(err_mean), ptr(var),
+         float(model_std), ptr(out), stream())
+    return out
+
+
+def zscore_targets(f_mean, f_var):
+    """reificationFusion.py:154-159 -> (z, zerr, stats[mean, std]) on the device."""
+    n = f_mean.numel()
+    z = torch.empty_like(f_mean)
+    zerr = torch.empty_like(f_mean)
+    stats = torch.empty((2,), dtype=F64, device=f_mean.device)
+    call("bf_zscore_targets", n, ptr(f_mean), ptr(f_var), ptr(z), ptr(zerr), ptr(stats), stream())
+    return z, zerr, stats
+
+
+# ---- k-medoids (util.py:38-49) -----------------------------------------------------------------
+def kmedoids_rowsum(X, row0=0, rows=None):
+    X = to_dev(X)
+    N, f = X.shape
+    rows = N - row0 if rows is None else rows
+    out = torch.empty((rows,), dtype=F64, device=X.device)
+    call("bf_kmedoids_rowsum", N, f, ptr(X), row0, rows, ptr(out), stream())
+    return out
+
+
+def kmedoids_fit(X, k, max_iter=300, rowsum=None):
+    """sklearn_extra KMedoids(k, random_state=0) defaults (oracle/kmedoids_shim.py): the
+    O(N^2) distance work runs on the device; the order-defining np.argpartition of the
+    heuristic init and the label sort run on host NumPy over N-vectors."""
+    Xd = to_dev(X)
+    N, f = Xd.shape
+    if k > N:
+        raise ValueError("The number of medoids (%d) must be less than the number of samples %d." % (k, N))
+    if rowsum is None:
+        rowsum = kmedoids_rowsum(Xd)
+    med = np.argpartition(rowsum.cpu().numpy(), k - 1)[:k].astype(np.int64)
+    med_d = to_dev(med, torch.int64)
+    labels = torch.empty((N,), dtype=torch.int32, device=Xd.device)
+    cost = torch.empty((N,), dtype=F64, device=Xd.device)
+    changed = torch.zeros((1,), dtype=torch.int32, device=Xd.device)
+    st = stream()
+    n_iter = 0
+    for n_iter in range(max_iter):
+        call("bf_kmedoids_assign", N, f, k, ptr(Xd), ptr(med_d), ptr(labels), st)
+        lab = labels.cpu().numpy()
+        perm = np.argsort(lab, kind="stable").astype(np.int64)
+        seg = np.zeros(k + 1, dtype=np.int64)
+        seg[1:] = np.cumsum(np.bincount(lab, minlength=k))
+        perm_d, seg_d = to_dev(perm, torch.int64), to_dev(seg, torch.int64)
+        call("bf_kmedoids_cluster_cost", N, f, k, ptr(Xd), ptr(perm_d), ptr(seg_d), ptr(cost), st)
+        changed.zero_()
+        call("bf_kmedoids_update", N, k, ptr(perm_d), ptr(seg_d), ptr(cost), ptr(med_d), ptr(changed), st)
+        if int(changed.item()) == 0:
+            break
+    call("bf_kmedoids_assign", N, f, k, ptr(Xd), ptr(med_d), ptr(labels), st)
+    return med_d.cpu().numpy(), labels.cpu().numpy().astype(np.int64), n_iter + 1

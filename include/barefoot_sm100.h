@@ -1,0 +1,160 @@
+/*
+ * barefoot_sm100.h - C ABI of libbarefoot_sm100.so, the B200 (sm_100a) implementation of
+ * BAREFOOT's data-parallel inner loop (GP posterior -> reification/fusion -> acquisition ->
+ * batch selection).
+ *
+ * The reference (/root/reference) has no FFI: its seam is a Python callable mapped over work
+ * items (barefoot.py:1070-1073, 1271-1283, 2001-2013).  Each export below replaces the numerics
+ * that one reference function runs on the CPU for ONE work item with a batched device call over
+ * all hyper-parameter sets x all candidates; the reference site is cited per function.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless it says "host"; FP64 (double) / int64 / int32,
+ *    row-major, contiguous.  The caller owns every buffer including workspace; the library never
+ *    allocates or frees device memory and keeps no global state except a thread-local error text.
+ *  - all launches are asynchronous on `stream` (a cudaStream_t passed as void*).
+ *  - return value: 0 = ok, < 0 = bad argument (BF_ERR_*), > 0 = a cudaError_t.
+ *  - "set" = one (hyper-parameter set[, fantasy point]) instance of a GP sharing the training
+ *    inputs X; `set_hp` (optional, may be NULL = identity) maps a set to its row of inv_l2/amp.
+ *  - np = n rounded up to a multiple of 32 (bf_padded_n).  Factor matrices are np x np row-major.
+ */
+#ifndef BAREFOOT_SM100_H
+#define BAREFOOT_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BF_VERSION 100
+
+/* covFunc: gpModel.py:29-36 */
+#define BF_KERN_SE  0
+#define BF_KERN_M32 1
+#define BF_KERN_M52 2
+
+/* acquisition mask bits for bf_gp_posterior (acquisitionFunc.py:98-214, util.py:655-665) */
+#define BF_ACQ_EI     1
+#define BF_ACQ_PI     2
+#define BF_ACQ_UCB    4
+#define BF_ACQ_GREEDY 8   /* also produces the top-2 of the mean that bf_kg_diag needs */
+/* slots of best_val / best_idx rows written by bf_acq_finalize */
+#define BF_SLOT_EI     0
+#define BF_SLOT_PI     1
+#define BF_SLOT_UCB    2
+#define BF_SLOT_GREEDY 3
+#define BF_SLOT_TOP2   4  /* value only: second largest mean (by position) */
+#define BF_NSLOT_VAL   5
+#define BF_NSLOT_IDX   4
+
+#define BF_ERR_ARG      (-1)
+#define BF_ERR_SIZE     (-2)   /* n, d or m outside what the kernels support */
+#define BF_ERR_ALIGN    (-3)
+
+#define BF_MAX_DIM      16     /* nDim supported by the cross-covariance generators */
+#define BF_MAX_MODELS   8      /* m supported by bf_reification */
+
+int         bf_version(void);
+const char* bf_last_error(void);
+
+/* ---- layout helpers (host side, pure arithmetic) ------------------------------------------ */
+int    bf_padded_n(int n);                 /* np: n rounded up to 32 */
+size_t bf_linv_packed_doubles(int n);      /* doubles per set of the packed L^-1 operand */
+int    bf_posterior_tile(int n);           /* candidates per CTA chosen for this n (0: too large) */
+int    bf_posterior_tiles(int n, long long N); /* CTAs per set = ceil(N / tile) */
+
+/* ---- (1)+(2) setup of a GP: gpModel.py:17-42 (george GP.compute) --------------------------- */
+/* K[s] = amp * k(X, X; inv_l2) + diag((sqrt(yerr^2 + 1.25e-12))^2), written as an np x np
+ * matrix padded with the identity.  noise is per set (noise_stride = n), shared (noise_stride =
+ * 0, n values) or scalar (noise_n = 1). */
+int bf_kernel_matrix(int kern, int n, int d, int S,
+                     const double* X, const double* inv_l2, const double* amp,
+                     const int32_t* set_hp,
+                     const double* yerr, int yerr_n, long long yerr_stride,
+                     double* K, void* stream);
+
+/* In-place lower Cholesky of S padded np x np matrices (george BasicSolver.compute ->
+ * scipy.linalg.cholesky, reached from gpModel.py:41).  info[s] = 0 or 1 + index of the first
+ * non-positive pivot (george would raise LinAlgError). */
+int bf_cholesky_batched(int n, int S, double* K_inout_L, int32_t* info, void* stream);
+
+/* L^-1 (row-major np x np into Linv, and the tensor-core operand layout into linv_packed) and
+ * alpha = K^-1 y (george GP._compute_alpha -> cho_solve, reached from gpModel.py:47,53).
+ * y is per set (y_stride = n) or shared (y_stride = 0). */
+int bf_factor_finish(int n, int S, const double* L, const double* y, long long y_stride,
+                     double* Linv, double* linv_packed, double* alpha, void* stream);
+
+/* ---- (1)+(2)+(4) posterior + elementwise acquisitions: gpModel.py:50-54,
+ * reificationFusion.py:189-206, acquisitionFunc.py:98-214 ------------------------------------ */
+/* For every set s and candidate c: k* = amp k(x*_c, X); mu = k*.alpha; var = amp - |L^-1 k*|^2;
+ * mu' = mu * scale[s] + shift[s]; var' = var * scale[s]^2 (scale/shift may be NULL = 1/0).
+ * mu_out / var_out ([S x N]) are optional.  If acq_mask != 0 the per-tile partial maxima are
+ * written to part_val [S x tiles x 5] / part_idx [S x tiles x 4]; reduce with bf_acq_finalize.
+ * spread_is_sqrt: PI/UCB receive sqrt(var') (ROM stage, util.py:451,519) instead of var'
+ * (TM/batch stage, util.py:598-612).  EI always receives var' (util.py:323-326). */
+int bf_gp_posterior(int kern, long long N, int n, int d, int S,
+                    const double* Xs, const double* X,
+                    const double* inv_l2, const double* amp, const int32_t* set_hp,
+                    const double* linv_packed, const double* alpha,
+                    const double* scale, const double* shift,
+                    double* mu_out, double* var_out,
+                    int acq_mask, int spread_is_sqrt, double curr_max, double xi, double kt,
+                    double* part_val, long long* part_idx, void* stream);
+
+/* Reduce per-tile partials: best_val [S x 5], best_idx [S x 4]; first index wins ties
+ * (np.where(v == max)[0][0], acquisitionFunc.py:135-138). */
+int bf_acq_finalize(int S, int tiles, int acq_mask, const double* part_val,
+                    const long long* part_idx, double* best_val, long long* best_idx,
+                    void* stream);
+
+/* ---- (4) knowledge gradient as the reference calls it, i.e. on np.diag(var):
+ * acquisitionFunc.py:12-96 via util.py:259-262,618-621 ---------------------------------------- */
+/* mu, var [S x N]; top [S x 5] / top_idx [S x 4] as written by bf_acq_finalize with
+ * BF_ACQ_GREEDY (slot GREEDY = largest mean and its first index, slot TOP2 = second largest).
+ * Candidates i < M are scored.  Output: kg_val[S], kg_idx[S] with the reference's floor (0, 0).
+ * part_* are [S x tiles] scratch, tiles = bf_kg_tiles(N).  nu_out ([S x N], optional) receives
+ * every log-KG value. */
+int bf_kg_tiles(long long N);
+int bf_kg_diag(long long N, long long M, int S, const double* mu, const double* var,
+               const double* top, const long long* top_idx, double sn,
+               double* nu_out, double* part_val, long long* part_idx,
+               double* kg_val, long long* kg_idx, void* stream);
+
+/* ---- (3) reification: reificationFusion.py:26-57 ------------------------------------------- */
+/* y, var: [m x P] (model-major).  mean_f, var_f: [P].  pinv semantics of numpy (rcond 1e-15). */
+int bf_reification(int m, long long P, const double* y, const double* var,
+                   double* mean_f, double* var_f, void* stream);
+
+/* ---- (5) k-medoids primitives for kmedoids_max: util.py:38-49 (sklearn_extra KMedoids) ------ */
+/* rowsum[i] = sum_j |x_i - x_j| for rows [row0, row0 + rows) against all N rows. */
+int bf_kmedoids_rowsum(long long N, int f, const double* X, long long row0, long long rows,
+                       double* rowsum, void* stream);
+/* labels[i] = first argmin_c |x_i - x_medoid[c]| */
+int bf_kmedoids_assign(long long N, int f, int k, const double* X, const long long* medoid_idx,
+                       int32_t* labels, void* stream);
+/* perm: the rows sorted by (label, index); seg [k + 1]: segment offsets into perm.
+ * cost[p] = sum over q in the same segment of |x_perm[p] - x_perm[q]| (in segment order). */
+int bf_kmedoids_cluster_cost(long long N, int f, int k, const double* X, const long long* perm,
+                             const long long* seg, double* cost, void* stream);
+/* Per cluster: first argmin of cost, and the alternate-method rule "move only if strictly
+ * better than the current medoid".  medoid_idx is updated in place; changed[0] counts moves. */
+int bf_kmedoids_update(long long N, int k, const long long* perm, const long long* seg,
+                       const double* cost, long long* medoid_idx, int32_t* changed, void* stream);
+
+/* ---- small on-device helpers for the fused-GP targets: reificationFusion.py:147-159 -------- */
+/* out[i] = a[i] * scale + shift */
+int bf_affine(long long n, const double* a, double scale, double shift, double* out, void* stream);
+/* total_var[i] = (err_mu[i] * err_std + err_mean)^2 + var[i] * model_std^2 (lines :148-152) */
+int bf_total_variance(long long n, const double* err_mu, double err_std, double err_mean,
+                      const double* var, double model_std, double* out, void* stream);
+/* z-score with the population std (np.std), std 0 -> 1 (lines :154-159):
+ * z = (f - mean) / std; zerr = |v / std^2|^0.5; stats[0] = mean, stats[1] = std. */
+int bf_zscore_targets(int n, const double* f_mean, const double* f_var, double* z, double* zerr,
+                      double* stats, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,61 @@
+"""CPU-only: the C-ABI library loads and exports every symbol the header declares
+(no compute call is made: there is no GPU in the build container)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "barefoot_sm100.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    from barefoot_framework_b200 import _lib
+    names = header_functions()
+    assert len(names) >= 20
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_library_exports_every_symbol():
+    from barefoot_framework_b200 import _lib
+    if not os.path.isfile(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = _lib.load()
+    for name in header_functions():
+        assert hasattr(lib, name), name
+    assert lib.bf_version() == 100
+    # pure host arithmetic helpers
+    assert lib.bf_padded_n(500) == 512 and lib.bf_padded_n(32) == 32 and lib.bf_padded_n(1) == 32
+    nb = 16
+    assert lib.bf_linv_packed_doubles(500) == 1024 * nb * (nb + 1) // 2
+    assert lib.bf_posterior_tile(500) == 48
+    assert lib.bf_posterior_tiles(500, 10 ** 6) == (10 ** 6 + 47) // 48
+    assert lib.bf_posterior_tile(5000) == 0
+
+
+def test_product_has_no_cpu_fallback():
+    """The product must fail loudly without CUDA rather than route through the oracle."""
+    import torch
+    from barefoot_framework_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(_lib.BarefootCudaError):
+        _lib.require_cuda()
+    from barefoot_framework_b200 import engine
+    with pytest.raises(_lib.BarefootCudaError):
+        engine.reification([[1.0, 2.0]], [[1.0, 1.0]])
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "barefoot_framework_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(".py"):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn

@@ -1,0 +1,272 @@
+"""GPU parity tests: every C-ABI kernel against the CPU oracle (oracle/fast.py) and the
+golden vectors of the verbatim reference.  Run on the B200 box: pytest -m gpu.
+
+Tolerances.  Indices / labels / medoids: bit-exact.  Posterior mean, variance and
+acquisition values: |delta| <= 1e-9 * max(|ref|, scale) where scale is the prior amplitude
+(variance, cancellation near training points - SURVEY.md 7.3) or max|ref| (mean)."""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import golden
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import fast  # noqa: E402
+
+REL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from barefoot_framework_b200 import engine
+    engine.device()
+    return engine
+
+
+def toy(x, shift=0.0):
+    return np.sum(np.sin(2 * np.pi * (x + shift)), axis=1) + 0.3 * np.sum(x, axis=1)
+
+
+def make_problem(rng, n, d, N):
+    X = np.round(rng.uniform(size=(n, d)), 5)
+    y = toy(X) + 0.05 * rng.normal(size=n)
+    y = (y - y.mean()) / y.std()
+    Xs = np.round(rng.uniform(size=(N, d)), 5)
+    Xs[: min(3, n)] = X[: min(3, n)]
+    return X, y, Xs
+
+
+def unpack_linv(packed, n):
+    """Invert the tensor-core operand layout (bf_common.cuh: bf_linv_elem_off)."""
+    np_ = (n + 31) // 32 * 32
+    i, j = np.tril_indices(np_)
+    b, t, r, g, kk = i >> 5, (i & 31) >> 3, i & 7, j >> 2, j & 3
+    off = 1024 * b * (b + 1) // 2 + ((g * 2 + (t >> 1)) * 32 + (r * 4 + kk)) * 2 + (t & 1)
+    out = np.zeros((np_, np_))
+    out[i, j] = packed[off]
+    return out
+
+
+@pytest.mark.parametrize("kern", ["SE", "M32", "M52"])
+@pytest.mark.parametrize("n,d", [(5, 1), (33, 2), (70, 3), (200, 6)])
+def test_setup_kernels(eng, kern, n, d):
+    rng = np.random.default_rng(n * 7 + d)
+    X, y, _ = make_problem(rng, n, d, 4)
+    H = 3
+    l = rng.uniform(0.15, 0.8, size=(H, d))
+    sf = rng.uniform(0.5, 3.0, size=H)
+    yerr = rng.uniform(0.03, 0.2, size=n)
+    f = eng.build_factors(kern, X, y, l ** 2, sf, yerr, keep_dense=True)
+    L = f.L.cpu().numpy()
+    Linv = f.Linv.cpu().numpy()
+    alpha = f.alpha.cpu().numpy()
+    packed = f.linv_packed.cpu().numpy()
+    for h in range(H):
+        g = fast.GP(X, y, l[h], sf[h], yerr, d, kern)
+        Lref = np.linalg.cholesky(g.K)
+        np.testing.assert_allclose(L[h, :n, :n], Lref, rtol=1e-10, atol=1e-12)
+        # identity padding
+        np_ = L.shape[1]
+        assert np.array_equal(L[h, n:, n:], np.eye(np_ - n))
+        assert not L[h, n:, :n].any()
+        Liref = np.linalg.inv(Lref)
+        scale = np.abs(Liref).max()
+        assert np.abs(Linv[h, :n, :n] - Liref).max() <= 1e-9 * scale
+        assert not np.triu(Linv[h], 1).any()
+        up = unpack_linv(packed[h], n)
+        assert np.array_equal(up, Linv[h])
+        assert np.abs(alpha[h] - g.alpha).max() <= 1e-9 * np.abs(g.alpha).max()
+
+
+def test_cholesky_reports_non_positive_definite(eng):
+    X = np.array([[0.1], [0.1], [0.5]])     # duplicated point, zero noise -> singular
+    with pytest.raises(np.linalg.LinAlgError):
+        # jitter 1.25e-12 keeps it barely PD in exact arithmetic; a negative amplitude cannot be
+        eng.build_factors("SE", X, np.zeros(3), [[1.0]], [-1.0], 0.0)
+
+
+@pytest.mark.parametrize("kern", ["SE", "M32", "M52"])
+@pytest.mark.parametrize("n,d,N", [(5, 1, 100), (33, 2, 257), (150, 6, 1000), (500, 6, 3000),
+                                   (700, 4, 500), (1100, 3, 200)])
+def test_posterior_mean_variance(eng, kern, n, d, N):
+    rng = np.random.default_rng(n + d + N)
+    X, y, Xs = make_problem(rng, n, d, N)
+    H = 2
+    l = rng.uniform(0.2, 0.9, size=(H, d))
+    sf = rng.uniform(0.5, 3.0, size=H)
+    f = eng.build_factors(kern, X, y, l ** 2, sf, 0.05)
+    res = eng.posterior_sweep(f, Xs, want_mu=True, want_var=True)
+    mu, var = res.mu.cpu().numpy(), res.var.cpu().numpy()
+    for h in range(H):
+        g = fast.GP(X, y, l[h], sf[h], 0.05, d, kern)
+        mref, vref = g.predict_var(Xs)
+        amp = sf[h] / d
+        assert np.abs(mu[h] - mref).max() <= REL * max(1.0, np.abs(mref).max())
+        assert np.abs(var[h] - vref).max() <= REL * amp
+
+
+def test_posterior_golden_reference_gp(eng):
+    """gp_model of the verbatim reference (gpModel.py on the george restatement)."""
+    g = golden("gp.npz")
+    for k in range(int(g["ncases"])):
+        d = int(g[f"d_{k}"])
+        sn = g[f"sn_{k}"]
+        f = eng.build_factors(str(g[f"kern_{k}"]), g[f"x_{k}"], g[f"y_{k}"], g[f"l_{k}"][None] ** 2,
+                              [float(g[f"sf_{k}"])], sn if sn.ndim else float(sn), ndim=d)
+        res = eng.posterior_sweep(f, g[f"xs_{k}"], want_mu=True, want_var=True)
+        amp = float(g[f"sf_{k}"]) / d
+        mref, vref = g[f"mu_{k}"], g[f"var_{k}"]
+        assert np.abs(res.mu[0].cpu().numpy() - mref).max() <= REL * max(1.0, np.abs(mref).max())
+        assert np.abs(res.var[0].cpu().numpy() - vref).max() <= REL * amp
+
+
+@pytest.mark.parametrize("stage", ["TM", "ROM"])
+@pytest.mark.parametrize("kern", ["SE", "M52"])
+def test_fused_acquisitions_select_like_the_oracle(eng, kern, stage):
+    rng = np.random.default_rng(11)
+    n, d, N, H = 120, 4, 5000, 5
+    X, y, Xs = make_problem(rng, n, d, N)
+    l = rng.uniform(0.2, 0.9, size=(H, d))
+    sf = rng.uniform(0.5, 3.0, size=H)
+    f = eng.build_factors(kern, X, y, l ** 2, sf, 0.05)
+    scale = torch.full((H,), 1.7, dtype=torch.float64, device="cuda")
+    shift = torch.full((H,), -0.4, dtype=torch.float64, device="cuda")
+    curr_max = 0.9
+    for name in ("EI", "PI", "UCB", "Greedy", "KG"):
+        v, i, _ = eng.acquisition_sweep(f, Xs, name, stage, curr_max, 3, scale, shift)
+        v, i = v.cpu().numpy(), i.cpu().numpy()
+        for h in range(H):
+            g = fast.GP(X, y, l[h], sf[h], 0.05, d, kern)
+            mu, var = g.predict_var(Xs)
+            mu, var = mu * 1.7 - 0.4, var * 1.7 ** 2
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                rv, ri = fast.acquisition(name, mu, var, curr_max, d, 3, stage)
+            assert int(i[h]) == ri, (name, h)
+            assert abs(v[h] - rv) <= REL * max(1.0, abs(rv)), (name, h, v[h], rv)
+
+
+def test_fused_argmax_is_consistent_with_stored_values(eng):
+    """Size-independent property: the fused per-tile reduction must pick exactly the first
+    maximum of the values the same launch stores (duplicates included)."""
+    rng = np.random.default_rng(5)
+    n, d, N = 64, 2, 20000
+    X, y, Xs = make_problem(rng, n, d, N)
+    Xs[7000:9000] = Xs[1000:3000]            # duplicated candidates -> exact ties
+    f = eng.build_factors("M32", X, y, [[0.3 ** 2, 0.4 ** 2]], [1.5], 0.05)
+    res = eng.posterior_sweep(f, Xs, want_mu=True, want_var=True, acq_mask=15, curr_max=0.5, kt=0.7)
+    mu, var = res.mu[0], res.var[0]
+    assert torch.equal(mu[7000:9000], mu[1000:3000]) and torch.equal(var[7000:9000], var[1000:3000])
+    best_val, best_idx = res.best_val[0].cpu().numpy(), res.best_idx[0].cpu().numpy()
+    mu_h, var_h = mu.cpu().numpy(), var.cpu().numpy()
+    top = np.sort(mu_h)[::-1]
+    assert best_val[3] == top[0] and best_val[4] == top[1]
+    assert best_idx[3] == int(np.where(mu_h == top[0])[0][0])
+    ucb = mu_h + 0.7 * var_h
+    assert best_idx[2] == int(np.where(ucb == ucb.max())[0][0])
+    assert abs(best_val[2] - ucb.max()) <= 1e-15 * abs(ucb.max()) * 4
+
+
+def test_kg_golden(eng):
+    """bf_kg_diag against knowledge_gradient(M, 0.1, mu, np.diag(var)) run verbatim."""
+    from barefoot_framework_b200 import _lib
+    g = golden("kg.npz")
+    for k in range(int(g["ncases"])):
+        mu, var, M = g[f"mu_{k}"], g[f"var_{k}"], int(g[f"M_{k}"])
+        N = mu.shape[0]
+        order = np.argsort(-mu, kind="stable")
+        top = np.zeros((1, 5))
+        top_idx = np.zeros((1, 4), dtype=np.int64)
+        top[0, 3] = mu[order[0]]
+        top[0, 4] = mu[order[1]] if N > 1 else -np.inf
+        top_idx[0, 3] = order[0]
+        res = eng.SweepResult()
+        res.mu, res.var = eng.to_dev(mu[None]), eng.to_dev(var[None])
+        res.best_val, res.best_idx = eng.to_dev(top), eng.to_dev(top_idx, torch.int64)
+        v, i, nu = eng.kg_from_sweep(res, M=M, want_nu=True)
+        assert int(i[0]) == int(g[f"x_star_{k}"]), k
+        ref = float(g[f"nu_star_{k}"])
+        assert abs(float(v[0]) - ref) <= REL * max(1.0, abs(ref)), k
+        nu = nu[0].cpu().numpy()[:M]
+        NU = g[f"NU_{k}"]
+        fin = np.isfinite(NU)
+        assert np.array_equal(np.isfinite(nu), fin), k
+        assert np.abs(nu[fin] - NU[fin]).max(initial=0) <= REL * np.abs(NU[fin]).max(initial=1.0)
+
+
+def cond_of(y, s):
+    sig = fast.reification_matrix(y, s)
+    return np.linalg.cond(sig)
+
+
+def test_reification_golden(eng):
+    g = golden("reification.npz")
+    for tag in ("m2", "m3", "m4", "m5", "edge"):
+        y, s = g[f"y_{tag}"], g[f"s_{tag}"]
+        mean, var = eng.reification(y, s)
+        mean, var = mean.cpu().numpy(), var.cpu().numpy()
+        cond = cond_of(y, s)
+        ok = cond < 1e5                      # where 1e-9 is attainable
+        mref, vref = g[f"mean_{tag}"], g[f"var_{tag}"]
+        yscale = np.abs(y).max(axis=0)
+        assert ok.sum() >= 0.5 * ok.size
+        assert (np.abs(mean - mref)[ok] <= REL * np.maximum(1.0, yscale[ok])).all(), tag
+        assert (np.abs(var - vref)[ok] <= REL * np.abs(vref[ok])).all(), tag
+        # ill-conditioned points: error bounded by cond * eps
+        bad = ~ok & np.isfinite(cond) & (cond < 1e13)
+        if bad.any():
+            assert (np.abs(var - vref)[bad] <= cond[bad] * 1e-14 * np.abs(vref[bad]) + 1e-300).all(), tag
+
+
+def test_reification_singular_points_use_pinv_semantics(eng):
+    """Identical models: the matrix is exactly singular; pinv gives the common mean and the
+    common variance (inv would fail)."""
+    y = np.tile(np.array([[0.3, -1.2, 2.0]]), (3, 1))
+    s = np.tile(np.array([[0.5, 0.1, 2.0]]), (3, 1))
+    mean, var = eng.reification(y, s)
+    ref_m, ref_v = fast.reification(y, s)
+    np.testing.assert_allclose(mean.cpu().numpy(), ref_m, rtol=1e-12)
+    np.testing.assert_allclose(var.cpu().numpy(), ref_v, rtol=1e-12)
+
+
+def test_targets_helpers(eng):
+    rng = np.random.default_rng(3)
+    a = rng.normal(size=777)
+    b = rng.uniform(0.1, 2, size=777)
+    out = eng.affine(eng.to_dev(a), 1.3, -0.2).cpu().numpy()
+    assert np.array_equal(out, a * 1.3 + -0.2)
+    tv = eng.total_variance(eng.to_dev(a), 0.7, 0.1, eng.to_dev(b), 1.25).cpu().numpy()
+    np.testing.assert_allclose(tv, (a * 0.7 + 0.1) ** 2 + b * (1.25 ** 2), rtol=1e-15)
+    z, zerr, stats = eng.zscore_targets(eng.to_dev(a), eng.to_dev(b))
+    sd = np.std(a)
+    np.testing.assert_allclose(stats.cpu().numpy(), [np.mean(a), sd], rtol=1e-13, atol=1e-16)
+    np.testing.assert_allclose(z.cpu().numpy(), (a - np.mean(a)) / sd, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(zerr.cpu().numpy(), np.abs(b / sd ** 2) ** 0.5, rtol=1e-13)
+
+
+def test_kmedoids_golden(eng):
+    g = golden("kmedoids.npz")
+    from barefoot_framework_b200 import util
+    np.testing.assert_array_equal(util.kmedoids_max(g["X3"], int(g["k3"])), g["med3"])
+    np.testing.assert_array_equal(util.kmedoids_max(g["X2"], int(g["k2"])), g["med2"])
+
+
+@pytest.mark.parametrize("N,f,k", [(500, 3, 7), (2000, 2, 10), (4097, 3, 5)])
+def test_kmedoids_matches_oracle(eng, N, f, k):
+    rng = np.random.default_rng(N + f)
+    cols = [np.exp(rng.normal(size=N)), rng.permutation(10 * N)[:N].astype(float)]
+    if f == 3:
+        cols.append(rng.integers(0, 3, size=N).astype(float))
+    X = np.column_stack(cols)
+    from oracle.kmedoids_shim import KMedoids, pairwise_euclidean
+    rs = eng.kmedoids_rowsum(X).cpu().numpy()
+    ref_rs = pairwise_euclidean(X).sum(axis=1)
+    np.testing.assert_allclose(rs, ref_rs, rtol=1e-9)
+    med, labels, n_iter = eng.kmedoids_fit(X, k)
+    km = KMedoids(n_clusters=k, random_state=0).fit(X)
+    np.testing.assert_array_equal(med, km.medoid_indices_)
+    np.testing.assert_array_equal(labels, km.labels_)
+    assert n_iter == km.n_iter_
