@@ -35,7 +35,10 @@ SIGNATURES = {
                               c_p, c_p, c_i, c_i, c_d, c_d, c_d, c_p, c_p, c_p]),
     "bf_acq_finalize": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "bf_kg_tiles": (c_i, [c_ll]),
+    "bf_top2": (c_i, [c_ll, c_i, c_p, c_p, c_p, c_p]),
     "bf_kg_diag": (c_i, [c_ll, c_ll, c_i, c_p, c_p, c_p, c_p, c_d, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "bf_acq_tiles": (c_i, [c_ll]),
+    "bf_acq_eval": (c_i, [c_i, c_ll, c_i, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_p]),
     "bf_reification": (c_i, [c_i, c_ll, c_p, c_p, c_p, c_p, c_p]),
     "bf_kmedoids_rowsum": (c_i, [c_ll, c_i, c_p, c_ll, c_ll, c_p, c_p]),
     "bf_kmedoids_assign": (c_i, [c_ll, c_i, c_i, c_p, c_p, c_p, c_p]),
@@ -90,7 +93,7 @@ def stream():
 
 
 # kernels per exported call, for the launch counter
-_KERNELS_PER_CALL = {"bf_kg_diag": 2}
+_KERNELS_PER_CALL = {"bf_kg_diag": 2, "bf_acq_eval": 2}
 
 
 def call(name, *args):

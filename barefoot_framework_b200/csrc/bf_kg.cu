@@ -79,6 +79,41 @@ __global__ void __launch_bounds__(KG_THREADS) bf_kg_finalize_kernel(
     }
 }
 
+// top-2 of the mean "by position" for callers that hold mu in memory (the fused path gets it from
+// the posterior epilogue): one CTA per set, fixed-order tree so the result is deterministic.
+__global__ void __launch_bounds__(1024) bf_top2_kernel(long long N, const double* __restrict__ mu,
+                                                       double* __restrict__ top, long long* __restrict__ top_idx) {
+    const int set = blockIdx.x;
+    const double* m_ = mu + (size_t)set * N;
+    BfTop2 t = bf_top2_init();
+    for (long long i = threadIdx.x; i < N; i += blockDim.x) bf_top2_merge(t, m_[i], i, -INFINITY);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        const double t1 = __shfl_xor_sync(0xffffffffu, t.t1, m);
+        const long long i1 = __shfl_xor_sync(0xffffffffu, t.i1, m);
+        const double t2 = __shfl_xor_sync(0xffffffffu, t.t2, m);
+        bf_top2_merge(t, t1, i1, t2);
+    }
+    __shared__ BfTop2 red[32];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        BfTop2 a = red[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) bf_top2_merge(a, red[w].t1, red[w].i1, red[w].t2);
+        top[(size_t)set * BF_NSLOT_VAL + BF_SLOT_GREEDY] = a.t1;
+        top[(size_t)set * BF_NSLOT_VAL + BF_SLOT_TOP2] = a.t2;
+        top_idx[(size_t)set * BF_NSLOT_IDX + BF_SLOT_GREEDY] = a.i1;
+    }
+}
+
+extern "C" int bf_top2(long long N, int S, const double* mu, double* top, long long* top_idx, void* stream) {
+    BF_CHECK_ARG(N > 0 && S >= 0 && mu && top && top_idx, BF_ERR_ARG, "bf_top2: bad argument");
+    if (S == 0) return 0;
+    bf_top2_kernel<<<S, 1024, 0, (cudaStream_t)stream>>>(N, mu, top, top_idx);
+    BF_CHECK_LAUNCH("bf_top2");
+    return 0;
+}
+
 extern "C" int bf_kg_diag(long long N, long long M, int S, const double* mu, const double* var,
                           const double* top, const long long* top_idx, double sn, double* nu_out,
                           double* part_val, long long* part_idx, double* kg_val, long long* kg_idx,

@@ -215,6 +215,47 @@ def acquisition_sweep(f, Xs, name, stage, curr_max, iteration, scale=None, shift
     return res.best_val[:, slot], res.best_idx[:, slot], res
 
 
+def acq_eval(name, y, spread, curr_max=0.0, xi=XI, kt=0.0, want_all=True):
+    """Stand-alone EI / PI / UCB / Greedy on given vectors (acquisitionFunc.py:98-214):
+    y, spread [N] or [S, N].  Returns device tensors (best_val [S], best_idx [S], values [S, N])."""
+    y = to_dev(y)
+    y2 = y.reshape(1, -1) if y.dim() == 1 else y
+    S, N = y2.shape
+    sp = None
+    if spread is not None:
+        sp = to_dev(spread).reshape(S, N)
+    lib = _lib.load()
+    tiles = lib.bf_acq_tiles(N)
+    dev = y2.device
+    pv = torch.empty((S, tiles), dtype=F64, device=dev)
+    pi = torch.empty((S, tiles), dtype=torch.int64, device=dev)
+    bv = torch.empty((S,), dtype=F64, device=dev)
+    bi = torch.empty((S,), dtype=torch.int64, device=dev)
+    out = torch.empty((S, N), dtype=F64, device=dev) if want_all else None
+    st = stream()
+    for s0 in range(0, S, 65535):
+        sc = min(65535, S - s0)
+        call("bf_acq_eval", ACQ_BITS[name], N, sc, y2[s0:].data_ptr(),
+             None if sp is None else sp[s0:].data_ptr(), float(curr_max), float(xi), float(kt),
+             None if out is None else out[s0:].data_ptr(), pv[s0:].data_ptr(), pi[s0:].data_ptr(),
+             bv[s0:].data_ptr(), bi[s0:].data_ptr(), st)
+    return bv, bi, out
+
+
+def kg_diag(mu, var, M=None, sn=SN_KG, want_nu=True):
+    """knowledge_gradient(M, sn, mu, np.diag(var)) on given vectors [N] or [S, N]: a greedy pass
+    for the top-2 of the mean, then the closed form (bf_kg_diag)."""
+    mu = to_dev(mu)
+    mu2 = mu.reshape(1, -1) if mu.dim() == 1 else mu
+    S, N = mu2.shape
+    res = SweepResult()
+    res.mu, res.var = mu2, to_dev(var).reshape(S, N)
+    res.best_val = torch.full((S, NSLOT_VAL), float("-inf"), dtype=F64, device=mu2.device)
+    res.best_idx = torch.zeros((S, NSLOT_IDX), dtype=torch.int64, device=mu2.device)
+    call("bf_top2", N, S, ptr(mu2), ptr(res.best_val), ptr(res.best_idx), stream())
+    return kg_from_sweep(res, M=M, sn=sn, want_nu=want_nu)
+
+
 def reification(y, var):
     """reification(y, sig) (reificationFusion.py:26-57) on device tensors [m, P]."""
     y = to_dev(y)

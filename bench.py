@@ -294,6 +294,12 @@ def run_gpu(args):
                     "flop_per_launch": flop_per_launch,
                     "peak_source": "cuBLAS DGEMM 8192^3 (FP64 DMMA) measured in this run, best of 5; "
                                    "MEASURED_PEAKS.json holds no FP64 figure"}
+        tr = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tr):      # dram__bytes_read+write per launch from the committed ncu --set full capture
+            for k, v in json.load(open(tr)).items():
+                if k.startswith(roofline["kernel"]):
+                    roofline["traffic"] = v["dram_bytes_per_launch"]
+                    roofline["traffic_source"] = v["source"]
         peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.isfile(peaks):
             roofline["hbm_gbs_measured"] = json.load(open(peaks)).get("hbm_gbs")

@@ -117,10 +117,24 @@ int bf_acq_finalize(int S, int tiles, int acq_mask, const double* part_val,
  * part_* are [S x tiles] scratch, tiles = bf_kg_tiles(N).  nu_out ([S x N], optional) receives
  * every log-KG value. */
 int bf_kg_tiles(long long N);
+/* top [S x 5] / top_idx [S x 4]: fills slots GREEDY (largest mean, first index) and TOP2 from
+ * mu [S x N] for callers whose mean did not come out of bf_gp_posterior. */
+int bf_top2(long long N, int S, const double* mu, double* top, long long* top_idx, void* stream);
 int bf_kg_diag(long long N, long long M, int S, const double* mu, const double* var,
                const double* top, const long long* top_idx, double sn,
                double* nu_out, double* part_val, long long* part_idx,
                double* kg_val, long long* kg_idx, void* stream);
+
+/* ---- (4) stand-alone elementwise acquisitions on given vectors: expected_improvement
+ * (acquisitionFunc.py:130-138), probability_improvement (:172-176), upper_conf_bound (:210-214),
+ * greedy first arg-max (util.py:655-665) ------------------------------------------------------- */
+/* kind = exactly one BF_ACQ_* bit.  y, spread [S x N] (spread may be NULL for GREEDY).  out
+ * ([S x N], optional) receives every value; best_val / best_idx [S] the maximum and its FIRST
+ * index.  part_* are [S x tiles] scratch, tiles = bf_acq_tiles(N). */
+int bf_acq_tiles(long long N);
+int bf_acq_eval(int kind, long long N, int S, const double* y, const double* spread,
+                double curr_max, double xi, double kt, double* out, double* part_val,
+                long long* part_idx, double* best_val, long long* best_idx, void* stream);
 
 /* ---- (3) reification: reificationFusion.py:26-57 ------------------------------------------- */
 /* y, var: [m x P] (model-major).  mean_f, var_f: [P].  pinv semantics of numpy (rcond 1e-15). */
