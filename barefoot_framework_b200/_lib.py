@@ -33,6 +33,8 @@ SIGNATURES = {
     "bf_factor_finish": (c_i, [c_i, c_i, c_p, c_p, c_ll, c_p, c_p, c_p, c_p]),
     "bf_gp_posterior": (c_i, [c_i, c_ll, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
                               c_p, c_p, c_i, c_i, c_d, c_d, c_d, c_p, c_p, c_p]),
+    "bf_gp_solve_rows": (c_i, [c_i, c_ll, c_i, c_i, c_p, c_p, c_p, c_d, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "bf_gp_cov": (c_i, [c_i, c_ll, c_ll, c_i, c_i, c_p, c_p, c_p, c_d, c_p, c_p, c_p, c_ll, c_p]),
     "bf_acq_finalize": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "bf_kg_tiles": (c_i, [c_ll]),
     "bf_top2": (c_i, [c_ll, c_i, c_p, c_p, c_p, c_p]),
@@ -93,7 +95,7 @@ def stream():
 
 
 # kernels per exported call, for the launch counter
-_KERNELS_PER_CALL = {"bf_kg_diag": 2, "bf_acq_eval": 2}
+_KERNELS_PER_CALL = {"bf_kg_diag": 2, "bf_acq_eval": 2, "bf_gp_solve_rows": 3}
 
 
 def call(name, *args):

@@ -178,6 +178,48 @@ def posterior_sweep(f, Xs, scale=None, shift=None, want_mu=False, want_var=False
     return out
 
 
+def solve_rows(f, Xa, set_index=0, want_mean=True):
+    """Vt = k(Xa, X) L^-T (and the posterior mean) for one set of `f` (needs keep_dense factors)."""
+    if f.Linv is None:
+        raise ValueError("solve_rows needs factors built with keep_dense=True")
+    Xa = to_dev(Xa).reshape(len(Xa), -1)
+    A = Xa.shape[0]
+    lib = _lib.load()
+    np_ = lib.bf_padded_n(f.n)
+    Ap = (A + 31) // 32 * 32
+    Ks = torch.empty((Ap, np_), dtype=F64, device=Xa.device)
+    Vt = torch.empty((Ap, np_), dtype=F64, device=Xa.device)
+    mean = torch.empty((A,), dtype=F64, device=Xa.device) if want_mean else None
+    hp = int(f.set_hp[set_index].item()) if f.set_hp is not None else set_index
+    amp = float(f.amp[hp].item())
+    call("bf_gp_solve_rows", KERN[f.kern], A, f.n, f.d, ptr(Xa), ptr(f.X), f.inv_l2[hp].data_ptr(), amp,
+         f.Linv[set_index].data_ptr(), f.alpha[set_index].data_ptr(), ptr(Ks), ptr(Vt), ptr(mean), stream())
+    return Xa, Vt, mean, hp, amp
+
+
+def posterior_cov(f, Xa, Xb=None, set_index=0):
+    """gp_model.predict_cov (gpModel.py:44-48): posterior mean at Xa and the full covariance
+    between Xa and Xb (default Xb = Xa) for one set."""
+    Xa, Vta, mean, hp, amp = solve_rows(f, Xa, set_index)
+    if Xb is None:
+        Xb, Vtb = Xa, Vta
+    else:
+        Xb, Vtb, _, _, _ = solve_rows(f, Xb, set_index, want_mean=False)
+    A, B = Xa.shape[0], Xb.shape[0]
+    C = torch.empty((A, B), dtype=F64, device=Xa.device)
+    call("bf_gp_cov", KERN[f.kern], A, B, f.n, f.d, ptr(Xa), ptr(Xb), f.inv_l2[hp].data_ptr(), amp,
+         ptr(Vta), ptr(Vtb), ptr(C), B, stream())
+    return mean, C
+
+
+def kg_full(mu, sigma, M=None, sn=SN_KG):
+    raise NotImplementedError("knowledge gradient on a dense covariance (SURVEY.md 8f rank 3) is not built yet")
+
+
+def kg_full_from_factors(f, x_test, shift=0.0, sn=SN_KG):
+    raise NotImplementedError("knowledge gradient on a dense covariance (SURVEY.md 8f rank 3) is not built yet")
+
+
 def kg_from_sweep(res, M=None, sn=SN_KG, want_nu=False):
     """knowledge_gradient on np.diag(var) (acquisitionFunc.py:12-96 via util.py:259-262):
     needs a sweep run with want_mu, want_var and ACQ_GREEDY."""

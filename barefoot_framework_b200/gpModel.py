@@ -74,6 +74,11 @@ class gp_model:
             self.sigma_n = np.append(self.sigma_n, new_y_err)
         self.gp = self.create_gp()
 
+    def __copy__(self):
+        new = object.__new__(type(self))
+        new.__dict__.update(self.__dict__)      # shares the (immutable) device factors
+        return new
+
     # pickling: device factors are rebuilt on load (the reference pickles whole objects,
     # barefoot.py:997-999)
     def __getstate__(self):

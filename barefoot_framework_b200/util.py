@@ -3,14 +3,27 @@ meaning and return shapes, with the numerics routed to the sm_100a kernels (engi
 
 Where the reference maps ONE work item per (model jj, fantasy point kk, hyper-parameter set mm)
 through a process pool (barefoot.py:1070-1073, 1271-1283, 2001-2013), the ``*_batch`` functions
-here take the whole grid in one call; the per-item functions (``calculate_KG`` ... ``fused_calculate``,
-``batchAcquisitionFunc``) keep the reference signature for drop-in use and call the batch form
-with a grid of one."""
+here take the whole grid in one call: all sets are factorised together and swept by one
+posterior + acquisition launch.  The per-item functions (``calculate_KG`` ... ``fused_calculate``,
+``batchAcquisitionFunc``, ``evaluateFusedModel``) keep the reference's pickle-file signature for
+drop-in use and call the batch form with a grid of one."""
+from pickle import dump, load
+
 import numpy as np
+import torch
 
 from . import engine
+from .acquisitionFunc import thompson_sampling
+from .engine import ACQ_BITS, ACQ_EI, ACQ_GREEDY, ACQ_PI, ACQ_UCB, SLOT_EI, SLOT_GREEDY, SLOT_PI, SLOT_UCB
+
+XI_ROM = 0.01            # util.py:323-326 (calculate_EI), :449, :919
+SN_KG = 0.1              # util.py:260,619
+_SLOTS = {"EI": SLOT_EI, "PI": SLOT_PI, "UCB": SLOT_UCB, "Greedy": SLOT_GREEDY}
 
 
+# ---------------------------------------------------------------------------------------------
+# batch selection
+# ---------------------------------------------------------------------------------------------
 def kmedoids_max(input_arr, n_clust):
     """util.py:38-49: cluster with sklearn_extra KMedoids(n_clust, random_state=0) defaults and
     return, per cluster, the index of the first row of the WHOLE array whose column 0 equals the
@@ -26,3 +39,301 @@ def kmedoids_max(input_arr, n_clust):
             continue
         new_medoids.append(np.where(col0 == np.max(members))[0][0])
     return np.array(new_medoids)
+
+
+def call_model(param):
+    """util.py:51-55."""
+    return param["Model"](param["Input Values"])
+
+
+def storeObject(obj, filename):
+    with open(filename, 'wb') as f:
+        dump(obj, f)
+
+
+def checkInitInputs(*args, **kwargs):
+    pass
+
+
+def checkParameterInputs(*args, **kwargs):
+    pass
+
+
+# ---------------------------------------------------------------------------------------------
+# one sweep = posterior + acquisition(s) for every set
+# ---------------------------------------------------------------------------------------------
+def _sweep(f, scale, shift, x_test, names, stage, curr_max, iteration, xi, M=None):
+    """Run the fused posterior for every set of `f` and return {name: (values [S], indices [S])}
+    as host arrays, plus "max_mean" [S].  PI / UCB spread: sqrt(var) in the ROM stage
+    (util.py:451,519), var in the TM / batch / Hedge paths (util.py:598-612,1058-1072,764-789)."""
+    names = list(names)
+    need_kg = "KG" in names
+    need_ts = "TS" in names
+    mask = ACQ_GREEDY
+    for nm in names:
+        mask |= ACQ_BITS.get(nm, 0)
+    d = f.d
+    kt = engine.ucb_kt(d, iteration) if "UCB" in names else 0.0
+    res = engine.posterior_sweep(f, x_test, scale, shift, want_mu=need_kg or need_ts,
+                                 want_var=need_kg or need_ts, acq_mask=mask,
+                                 spread_is_sqrt=(stage == "ROM"), curr_max=curr_max, xi=xi, kt=kt)
+    out = {}
+    if need_kg:
+        v, i, _ = engine.kg_from_sweep(res, M=M, sn=SN_KG)
+        out["KG"] = (v.cpu().numpy(), i.cpu().numpy())
+    bv, bi = res.best_val.cpu().numpy(), res.best_idx.cpu().numpy()
+    for nm in names:
+        if nm in _SLOTS:
+            out[nm] = (bv[:, _SLOTS[nm]].copy(), bi[:, _SLOTS[nm]].copy())
+    out["max_mean"] = bv[:, SLOT_GREEDY].copy()
+    if need_ts:
+        # Thompson sampling draws from the host RNG per set, in set order, like the reference's
+        # work items would in a serial pool (acquisitionFunc.py:216-248)
+        mu, var = res.mu.cpu().numpy(), res.var.cpu().numpy()
+        tv, ti = np.empty(f.S), np.empty(f.S, dtype=np.int64)
+        for s in range(f.S):
+            tv[s], ti[s], _ = thompson_sampling(mu[s], np.sqrt(var[s]))
+        out["TS"] = (tv, ti)
+    return out
+
+
+_HEDGE_ORDER = ("KG", "TS", "EI", "Greedy", "PI", "UCB")      # util.py:626-654, 733-789
+
+
+# ---------------------------------------------------------------------------------------------
+# TM stage: fused_calculate for all hyper-parameter sets (util.py:543-669)
+# ---------------------------------------------------------------------------------------------
+def fused_calculate_batch(model, x_fused, hp_sets, kernel, x_test, curr_max, sampleOpt,
+                          iteration=1, xi=0.01, targets=None):
+    """Every work item of barefoot.py:1222-1283 in one device pass.  Returns (values [H],
+    indices [H]); for sampleOpt "Hedge" a list of H lists of six [value, index] pairs."""
+    x_test = np.asarray(x_test, dtype=np.float64)
+    f, scale, shift = model.create_fused_GP_batch(x_fused, hp_sets, kernel, targets=targets)
+    if sampleOpt == "Hedge":
+        r = _sweep(f, scale, shift, x_test, _HEDGE_ORDER, "TM", curr_max, iteration, xi)
+        return [[[r[nm][0][h], int(r[nm][1][h])] for nm in _HEDGE_ORDER] for h in range(f.S)]
+    name = sampleOpt if sampleOpt in ("KG", "TS", "EI", "PI", "UCB") else "Greedy"
+    r = _sweep(f, scale, shift, x_test, [name], "TM", curr_max, iteration, xi)
+    return r[name]
+
+
+def fused_calculate(param):
+    """util.py:543-669 with the reference's pickle-file work-item signature."""
+    with open("data/parameterSets/parameterSet{}".format(param[1]), 'rb') as fh:
+        data = load(fh)
+    with open("data/reificationObj", 'rb') as fh:
+        model_temp = load(fh)
+    (iteration, model_data, x_fused, fused_model_HP, kernel, x_test, curr_max, xi, sampleOpt) = data[param[0]]
+    out = fused_calculate_batch(model_temp, x_fused, np.asarray(fused_model_HP)[None], kernel, x_test,
+                                curr_max, sampleOpt, iteration, xi)
+    if sampleOpt == "Hedge":
+        return out[0], x_test.shape[0]
+    return [out[0][0], int(out[1][0])], x_test.shape[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# ROM stage: calculate_* for the (jj, kk, mm) grid (util.py:216-886)
+# ---------------------------------------------------------------------------------------------
+def rom_stage_batch(model, x_fused, hp_sets, kernel, x_test, new_mean, acq, cost, curr_max,
+                    iteration=1, true_sample_count=None, jj_list=None, kk_list=None):
+    """The ROM-stage grid of barefoot.py:1001-1073: for every model jj, fantasy point kk and
+    hyper-parameter set mm, update ROM jj with (x_test[kk], new_mean[jj][kk]), rebuild the fused
+    GP and evaluate `acq` over x_test.  Returns the rows [max fused mean, value / cost[jj], x*,
+    jj, kk, mm] in the reference's loop order (Greedy is not divided by the cost, util.py:876).
+    For "Hedge" returns six such row lists in the portfolio order [KG, TS, EI, Greedy, PI, UCB].
+
+    The fused targets of one (jj, kk) do not depend on mm; the H fused GPs of every (jj, kk)
+    are factorised and swept together (one set per (jj, kk, mm))."""
+    import copy
+    x_test = np.asarray(x_test, dtype=np.float64)
+    hp = np.atleast_2d(np.asarray(hp_sets, dtype=np.float64))
+    H = hp.shape[0]
+    N = x_test.shape[0]
+    M = N if true_sample_count is None else int(true_sample_count)
+    jj_list = list(range(model.num_models)) if jj_list is None else list(jj_list)
+    kk_list = list(range(N)) if kk_list is None else list(kk_list)
+    zs, zerrs, stats, keys = [], [], [], []
+    for jj in jj_list:
+        for kk in kk_list:
+            m2 = _fantasy_copy(model, copy)
+            m2.update_GP(np.expand_dims(x_test[kk], axis=0), np.expand_dims(np.array([new_mean[jj][kk]]), axis=0), jj)
+            z, zerr, st = m2.fused_targets_device(x_fused)
+            zs.append(z)
+            zerrs.append(zerr)
+            stats.append(st)
+            keys.append((jj, kk))
+    G = len(keys)
+    Z = torch.stack(zs).repeat_interleave(H, dim=0).contiguous()          # [G*H, F]
+    ZE = torch.stack(zerrs).repeat_interleave(H, dim=0).contiguous()
+    ST = torch.stack(stats)                                               # [G, 2] (mean, std)
+    scale = ST[:, 1].repeat_interleave(H).contiguous()
+    shift = ST[:, 0].repeat_interleave(H).contiguous()
+    set_hp = np.tile(np.arange(H, dtype=np.int32), G)
+    f = engine.build_factors(kernel, x_fused, Z, hp[:, 1:] ** 2, hp[:, 0], ZE, ndim=model.num_dim,
+                             set_hp=set_hp)
+    hedge = acq == "Hedge"
+    names = _HEDGE_ORDER if hedge else [acq if acq in ("KG", "TS", "EI", "PI", "UCB") else "Greedy"]
+    # calculate_GPHedge hands the variance to PI / UCB (util.py:764-789) and uses x_test.shape[0] for KG
+    r = _sweep(f, scale, shift, x_test, names, "TM" if hedge else "ROM", curr_max, iteration, XI_ROM,
+               M=(N if hedge else M))
+    rows = {nm: [] for nm in names}
+    s = 0
+    for (jj, kk) in keys:
+        for mm in range(H):
+            for nm in names:
+                val = r[nm][0][s]
+                if not (nm == "Greedy" and not hedge):
+                    val = val / cost[jj]
+                row = [r["max_mean"][s], val, int(r[nm][1][s]), jj, kk, mm]
+                if nm == "Greedy" and not hedge:
+                    # calculate_Greedy appends the coordinates of the maximum twice (util.py:878-884)
+                    row += list(x_test[int(r[nm][1][s])]) * 2
+                rows[nm].append(row)
+            s += 1
+    if hedge:
+        return [rows[nm] for nm in names]
+    return rows[names[0]]
+
+
+def _fantasy_copy(model, copy):
+    """A model_reification whose ROM GPs can be updated without touching `model` (the reference
+    gets this from unpickling data/reificationObj per work item, util.py:236-237)."""
+    m2 = copy.copy(model)
+    m2.x_train = [np.array(x) for x in model.x_train]
+    m2.y_train = [np.array(y) for y in model.y_train]
+    m2.gp_models = [copy.copy(g) for g in model.gp_models]
+    return m2
+
+
+def _rom_item(param, acq):
+    with open("data/parameterSets/parameterSet{}".format(param[1]), 'rb') as fh:
+        data = load(fh)
+    with open("data/reificationObj", 'rb') as fh:
+        model_temp = load(fh)
+    (iteration, model_data, x_fused, fused_model_HP, kernel, x_test, jj, kk, mm, true_sample_count,
+     cost, curr_max) = data[param[0]]
+    new_mean = {jj: {kk: float(np.asarray(model_data[1]).reshape(-1)[0])}}
+    x_test = np.asarray(x_test, dtype=np.float64)
+    # the fantasy point travels in model_data; it is x_test[kk] in every reference call site
+    xt = x_test.copy()
+    xt_kk = np.asarray(model_data[0], dtype=np.float64).reshape(-1)
+    if not np.array_equal(xt[kk], xt_kk):
+        raise ValueError("model_data[0] must be x_test[kk] (barefoot.py:1005-1007)")
+    out = rom_stage_batch(model_temp, x_fused, np.asarray(fused_model_HP)[None], kernel, xt, new_mean, acq,
+                          cost, curr_max, iteration, true_sample_count, jj_list=[jj], kk_list=[kk])
+    if acq == "Hedge":
+        return [[o[0][0], o[0][1], o[0][2], jj, kk, mm] for o in out]
+    row = out[0]
+    return [row[0], row[1], row[2], jj, kk, mm] + list(row[6:])
+
+
+def calculate_KG(param):
+    """util.py:216-277."""
+    return _rom_item(param, "KG")
+
+
+def calculate_EI(param):
+    """util.py:279-341."""
+    return _rom_item(param, "EI")
+
+
+def calculate_TS(param):
+    """util.py:345-405."""
+    return _rom_item(param, "TS")
+
+
+def calculate_PI(param):
+    """util.py:407-469."""
+    return _rom_item(param, "PI")
+
+
+def calculate_UCB(param):
+    """util.py:471-541."""
+    return _rom_item(param, "UCB")
+
+
+def calculate_GPHedge(param):
+    """util.py:671-823."""
+    return _rom_item(param, "Hedge")
+
+
+def calculate_Greedy(param):
+    """util.py:825-886."""
+    return _rom_item(param, "Greedy")
+
+
+# ---------------------------------------------------------------------------------------------
+# batch-only path: batchAcquisitionFunc for all hyper-parameter sets (util.py:913-1129)
+# ---------------------------------------------------------------------------------------------
+def batch_acquisition_batch(modelGP, hp_sets, x_test, curr_max, acqFunc, iteration=1, xi=0.01):
+    """Every work item of barefoot.py:1966-2013 (reification=False) in one device pass.  The
+    hyper-parameters overwrite l_param WITHOUT squaring (util.py:948, quirk Q1).  Returns
+    (values [H], indices [H]), or the Hedge list of lists.  KG on this path uses the FULL
+    posterior covariance (util.py:1078-1081) and runs per set through bf_kg_full."""
+    x_test = np.asarray(x_test, dtype=np.float64)
+    hp = np.atleast_2d(np.asarray(hp_sets, dtype=np.float64))
+    x = np.asarray(modelGP.x_train, dtype=np.float64)
+    x = x.reshape(x.shape[0], -1)
+    y = np.asarray(modelGP.y_train, dtype=np.float64) - float(modelGP.mean)
+    f = engine.build_factors(modelGP.kern, x, y, hp[:, 1:], hp[:, 0], modelGP.sigma_n, ndim=modelGP.n_dim,
+                             keep_dense=acqFunc in ("KG", "Hedge"))
+    shift = None
+    if modelGP.mean:
+        shift = torch.full((f.S,), float(modelGP.mean), dtype=engine.F64, device=f.X.device)
+    scale = None if shift is None else torch.ones_like(shift)
+    if acqFunc in ("KG", "Hedge"):
+        names = [n for n in (_HEDGE_ORDER if acqFunc == "Hedge" else ()) if n != "KG"]
+        r = _sweep(f, scale, shift, x_test, names, "BATCH", curr_max, iteration, xi) if names else {}
+        kv, ki = engine.kg_full_from_factors(f, x_test, shift=float(modelGP.mean), sn=SN_KG)
+        r["KG"] = (kv, ki)
+        if acqFunc == "KG":
+            return r["KG"]
+        return [[[r[nm][0][h], int(r[nm][1][h])] for nm in _HEDGE_ORDER] for h in range(f.S)]
+    name = acqFunc if acqFunc in ("TS", "EI", "PI", "UCB") else "Greedy"
+    r = _sweep(f, scale, shift, x_test, [name], "BATCH", curr_max, iteration, xi)
+    return r[name]
+
+
+def batchAcquisitionFunc(param):
+    """util.py:913-1129 (single-objective branch) with the reference's work-item signature."""
+    with open("data/parameterSets/parameterSet{}".format(param[1]), 'rb') as fh:
+        data = load(fh)
+    with open("data/reificationObj", 'rb') as fh:
+        modelGP = load(fh)
+    iteration, x_test, fusedModelHP, curr_max, acqFunc, extra = data[param[0]]
+    if isinstance(modelGP, list):
+        raise NotImplementedError("multi-objective EHVI is outside the B200 hot path (DESIGN.md section 7)")
+    out = batch_acquisition_batch(modelGP, np.asarray(fusedModelHP)[None], x_test, curr_max, acqFunc, iteration)
+    if acqFunc == "Hedge":
+        return out[0]
+    return [out[0][0], int(out[1][0])]
+
+
+def evaluate_fused_model_batch(model, reification, x_fused, hp_sets, kernel, x_test):
+    """evaluateFusedModel (util.py:889-911) for all sets: the fused (or single-GP) posterior
+    mean at x_test, [H, N] on the host."""
+    hp = np.atleast_2d(np.asarray(hp_sets, dtype=np.float64))
+    if reification:
+        f, scale, shift = model.create_fused_GP_batch(x_fused, hp, kernel)
+    else:
+        x = np.asarray(model.x_train, dtype=np.float64)
+        x = x.reshape(x.shape[0], -1)
+        f = engine.build_factors(model.kern, x, np.asarray(model.y_train, dtype=np.float64) - float(model.mean),
+                                 hp[:, 1:], hp[:, 0], model.sigma_n, ndim=model.n_dim)
+        scale = shift = None
+    res = engine.posterior_sweep(f, np.asarray(x_test, dtype=np.float64), scale, shift, want_mu=True)
+    mu = res.mu.cpu().numpy()
+    if not reification and model.mean:
+        mu = mu + float(model.mean)
+    return mu
+
+
+def evaluateFusedModel(param):
+    """util.py:889-911."""
+    with open("data/parameterSets/parameterSet{}".format(param[1]), 'rb') as fh:
+        data = load(fh)
+    with open("data/reificationObj", 'rb') as fh:
+        model_temp = load(fh)
+    (finish, reification, x_fused, fused_model_HP, kernel, x_test, curr_max, xi, acqIndex) = data[param[0]]
+    mu = evaluate_fused_model_batch(model_temp, reification, x_fused, np.asarray(fused_model_HP)[None], kernel, x_test)
+    return [acqIndex, mu[0]]

@@ -125,6 +125,19 @@ int bf_kg_diag(long long N, long long M, int S, const double* mu, const double* 
                double* nu_out, double* part_val, long long* part_idx,
                double* kg_val, long long* kg_idx, void* stream);
 
+/* ---- full posterior covariance: gpModel.py:44-48 (george predict(..., return_cov=True)), called per
+ * hyper-parameter set by the batch-only path (util.py:952) -------------------------------------- */
+/* One set (pass that set's inv_l2 row, amp, Linv, alpha).  Ks, Vt: [Ap x np] scratch / output, Ap = A
+ * rounded up to 32.  Ks = amp k(Xa, X) zero padded; Vt = Ks L^-T (row a = L^-1 k(X, xa));
+ * mean[a] = Ks[a] . alpha (optional).  Linv is the row-major np x np L^-1 of bf_factor_finish. */
+int bf_gp_solve_rows(int kern, long long A, int n, int d, const double* Xa, const double* X,
+                     const double* inv_l2, double amp, const double* Linv, const double* alpha,
+                     double* Ks, double* Vt, double* mean, void* stream);
+/* C[a, b] = amp k(xa, xb) - Vta[a] . Vtb[b]  for a < A, b < B; C has leading dimension ldc. */
+int bf_gp_cov(int kern, long long A, long long B, int n, int d, const double* Xa, const double* Xb,
+              const double* inv_l2, double amp, const double* Vta, const double* Vtb, double* C,
+              long long ldc, void* stream);
+
 /* ---- (4) stand-alone elementwise acquisitions on given vectors: expected_improvement
  * (acquisitionFunc.py:130-138), probability_improvement (:172-176), upper_conf_bound (:210-214),
  * greedy first arg-max (util.py:655-665) ------------------------------------------------------- */
