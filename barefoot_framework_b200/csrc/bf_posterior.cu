@@ -4,7 +4,10 @@
 // probability_improvement / upper_conf_bound / greedy (acquisitionFunc.py:98-214,
 // util.py:655-665) for all hyper-parameter sets x all candidates in one launch.
 //
-// One CTA = one tile of NT candidates of one set:
+// One CTA = one tile of NT = 8 NTA candidates of one set.  The tile is sized so that TWO CTAs fit on
+// an SM whenever possible (NT = 24 at n = 500): FP64 DMMA and FP64 FMA share one SM pipe, so the only
+// way to keep it busy during the FP64-only phases A and C of one tile is the DMMA phase of another.
+// Phases:
 //   phase A  cross-covariance tile k*[np x NT] generated straight into shared memory in the
 //            DMMA B-fragment layout (never touches HBM); mean = k* . alpha folded in.
 //   phase B  V = L^-1 k* on the FP64 tensor cores (mma.sync m8n8k4 -> DMMA.8x8x4).  L^-1 is
@@ -30,62 +33,56 @@ struct PostParams {
 };
 
 // ---- phase A ------------------------------------------------------------------------------
-// Thread (warp w, lane): k-group g = w, w+8, ...; j = 4g + (lane & 3); candidate pair
-// c0 = 16 ap + (lane >> 2), c1 = c0 + 8.  Output cell ((g * NTA/2 + ap) * 32 + lane) * 2.
-template <int D>
+// B-tile layout: cell ((g * NTA + a) * 32 + lane) holds k*[4g + (lane & 3)][8a + (lane >> 2)], the
+// DMMA B fragment of atom a at k-group g.  Warp w generates k-groups g = w, w+8, ...
+template <int D, int NTA>
 __device__ __forceinline__ void gen_tile(const PostParams& p, const double* __restrict__ w_s,
                                          const double* __restrict__ xs_s, double* __restrict__ Bt,
                                          double* __restrict__ mpart, const double* __restrict__ alpha,
                                          double amp) {
+    constexpr int NT = 8 * NTA;
+    constexpr int DR = D ? D : BF_MAX_DIM;   // D == 0: nDim is a run-time value (9..16)
+    const int dd = D ? D : p.d;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kk = lane & 3, nn = lane >> 2;
-    const int NT = p.NT, NAP = p.NTA >> 1;
-    double w[D];
+    double w[DR];
 #pragma unroll
-    for (int a = 0; a < D; ++a) w[a] = w_s[a];
-    double macc[4][2];
+    for (int a = 0; a < DR; ++a) w[a] = a < dd ? w_s[a] : 0.0;
+    const double* xc = xs_s + nn;            // this lane's candidates: xc[a * NT + 8 * at]
+    double macc[NTA];
 #pragma unroll
-    for (int ap = 0; ap < 4; ++ap) macc[ap][0] = macc[ap][1] = 0.0;
+    for (int at = 0; at < NTA; ++at) macc[at] = 0.0;
 
     for (int g = warp; g < (p.np >> 2); g += BF_WARPS) {
         const int j = 4 * g + kk;
         const bool valid = j < p.n;
-        double xj[D];
+        double xj[DR];
 #pragma unroll
-        for (int a = 0; a < D; ++a) xj[a] = valid ? __ldg(p.X + (size_t)j * D + a) : 0.0;
+        for (int a = 0; a < DR; ++a) xj[a] = (valid && a < dd) ? __ldg(p.X + (size_t)j * dd + a) : 0.0;
         const double aj = valid ? __ldg(alpha + j) : 0.0;
-        double2* out = reinterpret_cast<double2*>(Bt) + (size_t)g * NAP * 32 + lane;
+        double* out = Bt + (size_t)g * NTA * 32 + lane;
 #pragma unroll
-        for (int ap = 0; ap < 4; ++ap) {
-            if (ap < NAP) {
-                const int c0 = 16 * ap + nn;
-                double r0 = 0.0, r1 = 0.0;
+        for (int at = 0; at < NTA; ++at) {
+            double r2 = 0.0;
 #pragma unroll
-                for (int a = 0; a < D; ++a) {
-                    const double d0 = xs_s[a * NT + c0] - xj[a];
-                    const double d1 = xs_s[a * NT + c0 + 8] - xj[a];
-                    r0 = fma(d0 * d0, w[a], r0);
-                    r1 = fma(d1 * d1, w[a], r1);
+            for (int a = 0; a < DR; ++a) {
+                if (a < dd) {
+                    const double df = xc[a * NT + 8 * at] - xj[a];
+                    r2 = fma(df * df, w[a], r2);
                 }
-                double2 v;
-                v.x = valid ? amp * bf_radial(p.kern, r0) : 0.0;
-                v.y = valid ? amp * bf_radial(p.kern, r1) : 0.0;
-                macc[ap][0] = fma(aj, v.x, macc[ap][0]);
-                macc[ap][1] = fma(aj, v.y, macc[ap][1]);
-                out[ap * 32] = v;
             }
+            const double v = valid ? amp * bf_radial(p.kern, r2) : 0.0;
+            macc[at] = fma(aj, v, macc[at]);
+            out[at * 32] = v;
         }
     }
     // mean partials: sum over the 4 kk lanes, then one slot per warp (fixed-order sum later)
 #pragma unroll
-    for (int ap = 0; ap < 4; ++ap) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            double v = macc[ap][q];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            if (kk == 0 && ap < NAP) mpart[warp * NT + 16 * ap + 8 * q + nn] = v;
-        }
+    for (int at = 0; at < NTA; ++at) {
+        double v = macc[at];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (kk == 0) mpart[warp * NT + 8 * at + nn] = v;
     }
 }
 
@@ -95,7 +92,7 @@ __device__ __forceinline__ void gen_tile(const PostParams& p, const double* __re
 // rows lie entirely above the columns of the group are skipped.
 template <int NA>
 __device__ __forceinline__ void mma_block(const double* __restrict__ Aset, const double* __restrict__ Bt,
-                                          int NAP_total, int a0, int b, double (&cs)[NA][2]) {
+                                          int NTA, int a0, int b, double (&cs)[NA][2]) {
     const int lane = threadIdx.x & 31;
     double c[4][NA][2];
 #pragma unroll
@@ -104,8 +101,8 @@ __device__ __forceinline__ void mma_block(const double* __restrict__ Aset, const
         for (int a = 0; a < NA; ++a) c[t][a][0] = c[t][a][1] = 0.0;
 
     const double2* Ap = reinterpret_cast<const double2*>(Aset + bf_linv_block_off(b)) + lane;
-    const double2* Bp = reinterpret_cast<const double2*>(Bt) + (size_t)(a0 >> 1) * 32 + lane;
-    const int gstride = NAP_total * 32;     // double2 per k-group in the B tile
+    const double* Bp = Bt + (size_t)a0 * 32 + lane;
+    const int gstride = NTA * 32;           // doubles per k-group in the B tile
     const int ng_full = 8 * b;              // groups left of the diagonal block
 
     double2 A0[2], A1[2];                   // ring of two k-groups: [tpair]
@@ -116,18 +113,14 @@ __device__ __forceinline__ void mma_block(const double* __restrict__ Aset, const
 
 #define BF_MMA_STEP(AR, G)                                                          \
     {                                                                               \
-        double2 bb[NA / 2];                                                         \
-        _Pragma("unroll") for (int ap = 0; ap < NA / 2; ++ap) bb[ap] =              \
-            Bp[(size_t)(G) * gstride + ap * 32];                                    \
-        _Pragma("unroll") for (int ap = 0; ap < NA / 2; ++ap) {                     \
-            bf_dmma(c[0][2 * ap][0], c[0][2 * ap][1], AR[0].x, bb[ap].x);           \
-            bf_dmma(c[1][2 * ap][0], c[1][2 * ap][1], AR[0].y, bb[ap].x);           \
-            bf_dmma(c[2][2 * ap][0], c[2][2 * ap][1], AR[1].x, bb[ap].x);           \
-            bf_dmma(c[3][2 * ap][0], c[3][2 * ap][1], AR[1].y, bb[ap].x);           \
-            bf_dmma(c[0][2 * ap + 1][0], c[0][2 * ap + 1][1], AR[0].x, bb[ap].y);   \
-            bf_dmma(c[1][2 * ap + 1][0], c[1][2 * ap + 1][1], AR[0].y, bb[ap].y);   \
-            bf_dmma(c[2][2 * ap + 1][0], c[2][2 * ap + 1][1], AR[1].x, bb[ap].y);   \
-            bf_dmma(c[3][2 * ap + 1][0], c[3][2 * ap + 1][1], AR[1].y, bb[ap].y);   \
+        double bb[NA];                                                              \
+        _Pragma("unroll") for (int a = 0; a < NA; ++a) bb[a] =                      \
+            Bp[(size_t)(G) * gstride + a * 32];                                     \
+        _Pragma("unroll") for (int a = 0; a < NA; ++a) {                            \
+            bf_dmma(c[0][a][0], c[0][a][1], AR[0].x, bb[a]);                        \
+            bf_dmma(c[1][a][0], c[1][a][1], AR[0].y, bb[a]);                        \
+            bf_dmma(c[2][a][0], c[2][a][1], AR[1].x, bb[a]);                        \
+            bf_dmma(c[3][a][0], c[3][a][1], AR[1].y, bb[a]);                        \
         }                                                                           \
     }
 
@@ -160,21 +153,17 @@ __device__ __forceinline__ void mma_block(const double* __restrict__ Aset, const
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int G = gg + h;
-            double2 bb[NA / 2];
+            double bb[NA];
 #pragma unroll
-            for (int ap = 0; ap < NA / 2; ++ap) bb[ap] = Bp[(size_t)(g + G) * gstride + ap * 32];
+            for (int a = 0; a < NA; ++a) bb[a] = Bp[(size_t)(g + G) * gstride + a * 32];
+            const double2 a01 = h ? A1[0] : A0[0];
+            const double2 a23 = h ? A1[1] : A0[1];
 #pragma unroll
-            for (int ap = 0; ap < NA / 2; ++ap) {
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const double bv = q ? bb[ap].y : bb[ap].x;
-                    const double2 a01 = h ? A1[0] : A0[0];
-                    const double2 a23 = h ? A1[1] : A0[1];
-                    if (G < 2) bf_dmma(c[0][2 * ap + q][0], c[0][2 * ap + q][1], a01.x, bv);
-                    if (G < 4) bf_dmma(c[1][2 * ap + q][0], c[1][2 * ap + q][1], a01.y, bv);
-                    if (G < 6) bf_dmma(c[2][2 * ap + q][0], c[2][2 * ap + q][1], a23.x, bv);
-                    bf_dmma(c[3][2 * ap + q][0], c[3][2 * ap + q][1], a23.y, bv);
-                }
+            for (int a = 0; a < NA; ++a) {
+                if (G < 2) bf_dmma(c[0][a][0], c[0][a][1], a01.x, bb[a]);
+                if (G < 4) bf_dmma(c[1][a][0], c[1][a][1], a01.y, bb[a]);
+                if (G < 6) bf_dmma(c[2][a][0], c[2][a][1], a23.x, bb[a]);
+                bf_dmma(c[3][a][0], c[3][a][1], a23.y, bb[a]);
             }
         }
         if (gg + 2 < 8) {
@@ -193,14 +182,18 @@ __device__ __forceinline__ void mma_block(const double* __restrict__ Aset, const
         }
 }
 
-template <int NA>
-__device__ __noinline__ void mma_phase(int nb, int NT, int NTA, const double* __restrict__ Aset,
+// Work units = (row-block pair) x (column slice of NA atoms); warps take units round-robin.  Unit
+// u: slice = u % nslices, pair = u / nslices.  Each warp owns one slice for the whole phase so its
+// column sums stay in registers; warps beyond the unit count idle.
+template <int NA, int MINB>
+__device__ __noinline__ void mma_phase(int nb, int NTA, const double* __restrict__ Aset,
                                        const double* __restrict__ Bt, double* __restrict__ spart) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int split = NTA / NA;                   // warps sharing a row-block pair
-    const int slice = warp % split;               // which NA atoms of the tile
-    const int wq = warp / split;                  // pair queue of this warp
-    const int nq = BF_WARPS / split;
+    const int NT = 8 * NTA;
+    const int nslices = NTA / NA;
+    const int nq = BF_WARPS / nslices;            // pair queues per slice
+    const int slice = warp % nslices, wq = warp / nslices;
+    if (wq >= nq) return;                         // spart was zeroed: idle warps contribute nothing
     const int npairs = (nb + 1) >> 1;
     const int a0 = slice * NA;
     double cs[NA][2];
@@ -208,8 +201,8 @@ __device__ __noinline__ void mma_phase(int nb, int NT, int NTA, const double* __
     for (int a = 0; a < NA; ++a) cs[a][0] = cs[a][1] = 0.0;
     for (int pr = wq; pr < npairs; pr += nq) {
         const int b_hi = nb - 1 - pr;
-        mma_block<NA>(Aset, Bt, NTA >> 1, a0, b_hi, cs);
-        if (pr != b_hi) mma_block<NA>(Aset, Bt, NTA >> 1, a0, pr, cs);
+        mma_block<NA>(Aset, Bt, NTA, a0, b_hi, cs);
+        if (pr != b_hi) mma_block<NA>(Aset, Bt, NTA, a0, pr, cs);
     }
     // column c = 8 (a0 + a) + 2 (lane & 3) + q; reduce over the 8 row lanes (lane >> 2)
 #pragma unroll
@@ -222,49 +215,50 @@ __device__ __noinline__ void mma_phase(int nb, int NT, int NTA, const double* __
             s += __shfl_xor_sync(0xffffffffu, s, 16);
             if ((lane >> 2) == 0) spart[wq * NT + 8 * (a0 + a) + 2 * (lane & 3) + q] = s;
         }
-    // queue slots >= nq are never written: the kernel zeroes spart before phase A
 }
 
-template <int D>
-__global__ void __launch_bounds__(BF_THREADS, 1) bf_posterior_kernel(PostParams p) {
+template <int D, int NTA, int MINB>
+__global__ void __launch_bounds__(BF_THREADS, MINB) bf_posterior_kernel(PostParams p) {
+    constexpr int NT = 8 * NTA;
     extern __shared__ __align__(16) double smem[];
+    const int dd = D ? D : p.d;
     double* Bt = smem;                                   // np * NT
-    double* xs_s = Bt + (size_t)p.np * p.NT;             // D * NT
-    double* mpart = xs_s + D * p.NT;                     // BF_WARPS * NT
-    double* spart = mpart + BF_WARPS * p.NT;             // BF_WARPS * NT
-    double* w_s = spart + BF_WARPS * p.NT;               // BF_MAX_DIM
+    double* xs_s = Bt + (size_t)p.np * NT;               // d * NT
+    double* mpart = xs_s + dd * NT;                      // BF_WARPS * NT
+    double* spart = mpart + BF_WARPS * NT;               // BF_WARPS * NT
+    double* w_s = spart + BF_WARPS * NT;                 // BF_MAX_DIM
     __shared__ BfBest red_best[4][2];
     __shared__ BfTop2 red_top[2];
 
     const int tile = blockIdx.x, set = blockIdx.y;
     const int hp = p.set_hp ? p.set_hp[set] : set;
-    const int NT = p.NT;
     const long long c_base = (long long)tile * NT;
     const double amp = p.amp[hp];
 
-    for (int e = threadIdx.x; e < D * NT; e += BF_THREADS) {
+    for (int e = threadIdx.x; e < dd * NT; e += BF_THREADS) {
         const int a = e / NT, c = e - a * NT;
         const long long gi = c_base + c;
-        xs_s[e] = gi < p.N ? p.Xs[gi * D + a] : 0.0;
+        xs_s[e] = gi < p.N ? p.Xs[gi * dd + a] : 0.0;
     }
     for (int e = threadIdx.x; e < BF_WARPS * NT; e += BF_THREADS) spart[e] = 0.0;
-    if (threadIdx.x < D) w_s[threadIdx.x] = p.inv_l2[(size_t)hp * D + threadIdx.x];
+    if (threadIdx.x < dd) w_s[threadIdx.x] = p.inv_l2[(size_t)hp * dd + threadIdx.x];
     __syncthreads();
 
-    gen_tile<D>(p, w_s, xs_s, Bt, mpart, p.alpha + (size_t)set * p.n, amp);
+    gen_tile<D, NTA>(p, w_s, xs_s, Bt, mpart, p.alpha + (size_t)set * p.n, amp);
     __syncthreads();
 
     const double* Aset = p.linv + (size_t)set * p.linv_stride;
     {
-        // widest column slice such that every warp has a row-block pair to work on
+        // widest column slice (a divisor of NTA) that still gives every pair queue a row-block pair
         const int npairs = (p.nb + 1) >> 1;
-        int NA = p.NTA;
-        while (NA > 2 && (NA % 4 == 0) && (BF_WARPS / (p.NTA / NA)) > npairs) NA >>= 1;
+        int NA = 1;
+        for (int cand = (MINB == 2 && NTA > 4) ? NTA / 2 : NTA; cand >= 1; --cand)   // 128-register budget
+            if (NTA % cand == 0 && (cand == 1 || BF_WARPS / (NTA / cand) <= npairs)) { NA = cand; break; }
         switch (NA) {
-            case 8: mma_phase<8>(p.nb, NT, p.NTA, Aset, Bt, spart); break;
-            case 6: mma_phase<6>(p.nb, NT, p.NTA, Aset, Bt, spart); break;
-            case 4: mma_phase<4>(p.nb, NT, p.NTA, Aset, Bt, spart); break;
-            default: mma_phase<2>(p.nb, NT, p.NTA, Aset, Bt, spart); break;
+            case 6: if (NTA == 6 && MINB == 1) mma_phase<6, MINB>(p.nb, NTA, Aset, Bt, spart); break;
+            case 3: if (NTA % 3 == 0) mma_phase<3, MINB>(p.nb, NTA, Aset, Bt, spart); break;
+            case 2: if (NTA % 2 == 0) mma_phase<2, MINB>(p.nb, NTA, Aset, Bt, spart); break;
+            default: mma_phase<1, MINB>(p.nb, NTA, Aset, Bt, spart); break;
         }
     }
     __syncthreads();
@@ -399,13 +393,19 @@ extern "C" size_t bf_linv_packed_doubles(int n) {
     return bf_linv_block_off(nb);
 }
 
-extern "C" int bf_posterior_tile(int n) {
+// Tile choice.  Preference: two CTAs per SM (the phases of one tile overlap the DMMA phase of the
+// other) with the widest tile that fits, then one CTA per SM.
+struct TileChoice { int NT; int minb; };
+static TileChoice choose_tile(int n) {
     const int np = bf_padded_n(n);
-    const int cand[4] = {64, 48, 32, 16};
-    for (int i = 0; i < 4; ++i)
-        if (posterior_smem_bytes(np, cand[i], BF_MAX_DIM) + 256 <= 227 * 1024) return cand[i];
-    return 0;
+    const size_t two = (size_t)(233472 / 2 - 1024 - 256), one = (size_t)227 * 1024 - 256;
+    const TileChoice pref[5] = {{48, 2}, {24, 2}, {48, 1}, {24, 1}, {16, 1}};
+    for (int i = 0; i < 5; ++i)
+        if (posterior_smem_bytes(np, pref[i].NT, BF_MAX_DIM) <= (pref[i].minb == 2 ? two : one)) return pref[i];
+    return TileChoice{0, 0};
 }
+
+extern "C" int bf_posterior_tile(int n) { return choose_tile(n).NT; }
 
 extern "C" int bf_posterior_tiles(int n, long long N) {
     int NT = bf_posterior_tile(n);
@@ -413,17 +413,26 @@ extern "C" int bf_posterior_tiles(int n, long long N) {
     return (int)((N + NT - 1) / NT);
 }
 
-template <int D>
+template <int D, int NTA, int MINB>
 static int launch_posterior(const PostParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(bf_posterior_kernel<D>,
+    cudaError_t e = cudaFuncSetAttribute(bf_posterior_kernel<D, NTA, MINB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         bf_set_error("bf_gp_posterior: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
         return (int)e;
     }
-    bf_posterior_kernel<D><<<grid, BF_THREADS, smem, st>>>(p);
+    bf_posterior_kernel<D, NTA, MINB><<<grid, BF_THREADS, smem, st>>>(p);
     BF_CHECK_LAUNCH("bf_gp_posterior");
     return 0;
+}
+
+template <int D>
+static int launch_posterior_tile(const PostParams& p, int minb, dim3 grid, size_t smem, cudaStream_t st) {
+    if (p.NT == 48 && minb == 2) return launch_posterior<D, 6, 2>(p, grid, smem, st);
+    if (p.NT == 24 && minb == 2) return launch_posterior<D, 3, 2>(p, grid, smem, st);
+    if (p.NT == 48) return launch_posterior<D, 6, 1>(p, grid, smem, st);
+    if (p.NT == 24) return launch_posterior<D, 3, 1>(p, grid, smem, st);
+    return launch_posterior<D, 2, 1>(p, grid, smem, st);
 }
 
 extern "C" int bf_gp_posterior(int kern, long long N, int n, int d, int S, const double* Xs,
@@ -442,7 +451,8 @@ extern "C" int bf_gp_posterior(int kern, long long N, int n, int d, int S, const
     if (N == 0 || S == 0) return 0;
     PostParams p;
     p.kern = kern; p.n = n; p.d = d; p.np = bf_padded_n(n); p.nb = p.np / 32;
-    p.NT = bf_posterior_tile(n);
+    const TileChoice tc = choose_tile(n);
+    p.NT = tc.NT;
     BF_CHECK_ARG(p.NT > 0, BF_ERR_SIZE, "bf_gp_posterior: n=%d too large for the shared-memory tile", n);
     p.NTA = p.NT / 8; p.S = S; p.N = N;
     p.Xs = Xs; p.X = X; p.inv_l2 = inv_l2; p.amp = amp; p.linv = linv_packed; p.alpha = alpha;
@@ -458,10 +468,10 @@ extern "C" int bf_gp_posterior(int kern, long long N, int n, int d, int S, const
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = posterior_smem_bytes(p.np, p.NT, d);
     switch (d) {
-#define BF_CASE(DD) case DD: return launch_posterior<DD>(p, grid, smem, st);
+#define BF_CASE(DD) case DD: return launch_posterior_tile<DD>(p, tc.minb, grid, smem, st);
         BF_CASE(1) BF_CASE(2) BF_CASE(3) BF_CASE(4) BF_CASE(5) BF_CASE(6) BF_CASE(7) BF_CASE(8)
-        BF_CASE(9) BF_CASE(10) BF_CASE(11) BF_CASE(12) BF_CASE(13) BF_CASE(14) BF_CASE(15) BF_CASE(16)
 #undef BF_CASE
+        default: return launch_posterior_tile<0>(p, tc.minb, grid, smem, st);   // nDim 9..16 at run time
     }
     return BF_ERR_SIZE;
 }

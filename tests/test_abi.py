@@ -34,8 +34,8 @@ def test_library_exports_every_symbol():
     assert lib.bf_padded_n(500) == 512 and lib.bf_padded_n(32) == 32 and lib.bf_padded_n(1) == 32
     nb = 16
     assert lib.bf_linv_packed_doubles(500) == 1024 * nb * (nb + 1) // 2
-    assert lib.bf_posterior_tile(500) == 48
-    assert lib.bf_posterior_tiles(500, 10 ** 6) == (10 ** 6 + 47) // 48
+    assert lib.bf_posterior_tile(500) == 24
+    assert lib.bf_posterior_tiles(500, 10 ** 6) == (10 ** 6 + 23) // 24
     assert lib.bf_posterior_tile(5000) == 0
 
 
