@@ -27,7 +27,7 @@ SIGNATURES = {
     "bf_padded_n": (c_i, [c_i]),
     "bf_linv_packed_doubles": (c_sz, [c_i]),
     "bf_posterior_tile": (c_i, [c_i]),
-    "bf_posterior_tiles": (c_i, [c_i, c_ll]),
+    "bf_posterior_parts": (c_i, [c_i, c_ll, c_i]),
     "bf_kernel_matrix": (c_i, [c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_p, c_p]),
     "bf_cholesky_batched": (c_i, [c_i, c_i, c_p, c_p, c_p]),
     "bf_factor_finish": (c_i, [c_i, c_i, c_p, c_p, c_ll, c_p, c_p, c_p, c_p]),

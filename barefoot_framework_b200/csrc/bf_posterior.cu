@@ -16,6 +16,8 @@
 //            Only the column sums of V^2 are kept.
 //   phase C  var = amp - |V|^2, de-normalise, acquisition values, per-tile (max, first index)
 //            and top-2 of the mean.
+#include <stdlib.h>
+
 #include "bf_common.cuh"
 
 struct PostParams {
@@ -29,7 +31,10 @@ struct PostParams {
     double curr_max, xi, kt;
     double* part_val;
     long long* part_idx;
-    int tiles;
+    int tiles;            // partial slots per set (= CTAs per set)
+    int tpc;              // tiles per CTA
+    long long ntiles;     // candidate tiles per set
+    int debug_skip;       // profiling only (BF_DEBUG_SKIP): 1 = no phase B, 2 = no phase A, 4 = no phase C
 };
 
 // ---- phase A ------------------------------------------------------------------------------
@@ -39,41 +44,63 @@ template <int D, int NTA>
 __device__ __forceinline__ void gen_tile(const PostParams& p, const double* __restrict__ w_s,
                                          const double* __restrict__ xs_s, double* __restrict__ Bt,
                                          double* __restrict__ mpart, const double* __restrict__ alpha,
-                                         double amp) {
+                                         double amp, const double* __restrict__ tab, int warp,
+                                         int nwarps = BF_WARPS) {
     constexpr int NT = 8 * NTA;
     constexpr int DR = D ? D : BF_MAX_DIM;   // D == 0: nDim is a run-time value (9..16)
     const int dd = D ? D : p.d;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     const int kk = lane & 3, nn = lane >> 2;
     double w[DR];
 #pragma unroll
-    for (int a = 0; a < DR; ++a) w[a] = a < dd ? w_s[a] : 0.0;
+    for (int a = 0; a < DR; ++a) w[a] = a < dd ? 0.5 * w_s[a] : 0.0;     // exact: h2 = r2 / 2
     const double* xc = xs_s + nn;            // this lane's candidates: xc[a * NT + 8 * at]
     double macc[NTA];
 #pragma unroll
     for (int at = 0; at < NTA; ++at) macc[at] = 0.0;
 
-    for (int g = warp; g < (p.np >> 2); g += BF_WARPS) {
-        const int j = 4 * g + kk;
-        const bool valid = j < p.n;
-        double xj[DR];
+    // G k-groups per trip: G * NTA independent (branch-free) evaluation chains per lane hide the
+    // latency of the FP64 pipe, which these warps share with the DMMA warps
+    constexpr int G = (NTA <= 3 && DR <= 8) ? 2 : 1;
+    const int ng = p.np >> 2;
+    for (int g0 = warp; g0 < ng; g0 += G * nwarps) {
+        double xj[G][DR], aj[G];
 #pragma unroll
-        for (int a = 0; a < DR; ++a) xj[a] = (valid && a < dd) ? __ldg(p.X + (size_t)j * dd + a) : 0.0;
-        const double aj = valid ? __ldg(alpha + j) : 0.0;
-        double* out = Bt + (size_t)g * NTA * 32 + lane;
+        for (int h = 0; h < G; ++h) {
+            const int j = 4 * (g0 + h * nwarps) + kk;
+            const bool valid = (g0 + h * nwarps) < ng && j < p.n;
 #pragma unroll
-        for (int at = 0; at < NTA; ++at) {
-            double r2 = 0.0;
+            for (int a = 0; a < DR; ++a) xj[h][a] = (valid && a < dd) ? __ldg(p.X + (size_t)j * dd + a) : 0.0;
+            aj[h] = valid ? __ldg(alpha + j) : 0.0;
+        }
+        double v[G][NTA];
 #pragma unroll
-            for (int a = 0; a < DR; ++a) {
-                if (a < dd) {
-                    const double df = xc[a * NT + 8 * at] - xj[a];
-                    r2 = fma(df * df, w[a], r2);
+        for (int h = 0; h < G; ++h)
+#pragma unroll
+            for (int at = 0; at < NTA; ++at) {
+                double h2 = 0.0;
+#pragma unroll
+                for (int a = 0; a < DR; ++a) {
+                    if (a < dd) {
+                        const double df = xc[a * NT + 8 * at] - xj[h][a];
+                        h2 = fma(df * df, w[a], h2);
+                    }
+                }
+                v[h][at] = amp * bf_radial_half(p.kern, h2, tab);
+            }
+#pragma unroll
+        for (int h = 0; h < G; ++h) {
+            const int g = g0 + h * nwarps;
+            if (g < ng) {
+                const bool valid = 4 * g + kk < p.n;
+                double* out = Bt + (size_t)g * NTA * 32 + lane;
+#pragma unroll
+                for (int at = 0; at < NTA; ++at) {
+                    const double val = valid ? v[h][at] : 0.0;
+                    macc[at] = fma(aj[h], val, macc[at]);
+                    out[at * 32] = val;
                 }
             }
-            const double v = valid ? amp * bf_radial(p.kern, r2) : 0.0;
-            macc[at] = fma(aj, v, macc[at]);
-            out[at * 32] = v;
         }
     }
     // mean partials: sum over the 4 kk lanes, then one slot per warp (fixed-order sum later)
@@ -90,7 +117,7 @@ __device__ __forceinline__ void gen_tile(const PostParams& p, const double* __re
 // One warp, one row block b, NA column atoms starting at atom a0: accumulates the column sums
 // of (L^-1[b,:] k*)^2 into cs.  The last 8 k-groups are the diagonal 32x32 block: atoms whose
 // rows lie entirely above the columns of the group are skipped.
-template <int NA>
+template <int NA, int R>
 __device__ __forceinline__ void mma_block(const double* __restrict__ Aset, const double* __restrict__ Bt,
                                           int NTA, int a0, int b, double (&cs)[NA][2]) {
     const int lane = threadIdx.x & 31;
@@ -105,70 +132,52 @@ __device__ __forceinline__ void mma_block(const double* __restrict__ Aset, const
     const int gstride = NTA * 32;           // doubles per k-group in the B tile
     const int ng_full = 8 * b;              // groups left of the diagonal block
 
-    double2 A0[2], A1[2];                   // ring of two k-groups: [tpair]
-    A0[0] = __ldg(Ap);
-    A0[1] = __ldg(Ap + 32);
-    A1[0] = __ldg(Ap + 64);
-    A1[1] = __ldg(Ap + 96);
-
-#define BF_MMA_STEP(AR, G)                                                          \
-    {                                                                               \
-        double bb[NA];                                                              \
-        _Pragma("unroll") for (int a = 0; a < NA; ++a) bb[a] =                      \
-            Bp[(size_t)(G) * gstride + a * 32];                                     \
-        _Pragma("unroll") for (int a = 0; a < NA; ++a) {                            \
-            bf_dmma(c[0][a][0], c[0][a][1], AR[0].x, bb[a]);                        \
-            bf_dmma(c[1][a][0], c[1][a][1], AR[0].y, bb[a]);                        \
-            bf_dmma(c[2][a][0], c[2][a][1], AR[1].x, bb[a]);                        \
-            bf_dmma(c[3][a][0], c[3][a][1], AR[1].y, bb[a]);                        \
-        }                                                                           \
-    }
-
-    int g = 0;
-    for (; g < ng_full; g += 2) {
-        double2 N0[2], N1[2];
-        const double2* An = Ap + (size_t)(g + 2) * 64;   // always in range: diagonal block follows
-        N0[0] = __ldg(An);
-        N0[1] = __ldg(An + 32);
-        N1[0] = __ldg(An + 64);
-        N1[1] = __ldg(An + 96);
-        BF_MMA_STEP(A0, g);
-        BF_MMA_STEP(A1, g + 1);
-        A0[0] = N0[0]; A0[1] = N0[1];
-        A1[0] = N1[0]; A1[1] = N1[1];
-    }
-#undef BF_MMA_STEP
-    // diagonal block: groups g .. g+7, group gg touches columns 4gg..4gg+3 of the block;
-    // atom t (rows 8t..8t+7) is non-zero only for gg < 2t + 2.
+    // A-operand ring: R (4 or 8) k-groups in registers; group g + R - 1 is requested while group g
+    // is multiplied, so R - 1 groups (4 NA DMMAs each) cover the L2 latency.  All trip counts and
+    // ring slots are compile-time so no DMMA sits behind a run-time predicate.
+    static_assert(R == 4 || R == 8, "ring depth must divide the 8 k-groups of a row block");
+    double2 ring[R][2];
 #pragma unroll
-    for (int gg = 0; gg < 8; gg += 2) {
-        double2 N0[2], N1[2];
-        if (gg + 2 < 8) {
-            const double2* An = Ap + (size_t)(g + gg + 2) * 64;
-            N0[0] = __ldg(An);
-            N0[1] = __ldg(An + 32);
-            N1[0] = __ldg(An + 64);
-            N1[1] = __ldg(An + 96);
-        }
+    for (int r = 0; r < R - 1; ++r) {       // at least the 8 diagonal groups exist
+        ring[r][0] = __ldg(Ap + (size_t)r * 64);
+        ring[r][1] = __ldg(Ap + (size_t)r * 64 + 32);
+    }
+    for (int g0 = 0; g0 < ng_full; g0 += R) {           // ng_full = 8 b is a multiple of R
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int G = gg + h;
+        for (int r = 0; r < R; ++r) {
+            const int g = g0 + r;
+            ring[(r + R - 1) % R][0] = __ldg(Ap + (size_t)(g + R - 1) * 64);   // in range: the diagonal block follows
+            ring[(r + R - 1) % R][1] = __ldg(Ap + (size_t)(g + R - 1) * 64 + 32);
             double bb[NA];
 #pragma unroll
-            for (int a = 0; a < NA; ++a) bb[a] = Bp[(size_t)(g + G) * gstride + a * 32];
-            const double2 a01 = h ? A1[0] : A0[0];
-            const double2 a23 = h ? A1[1] : A0[1];
+            for (int a = 0; a < NA; ++a) bb[a] = Bp[(size_t)g * gstride + a * 32];
 #pragma unroll
             for (int a = 0; a < NA; ++a) {
-                if (G < 2) bf_dmma(c[0][a][0], c[0][a][1], a01.x, bb[a]);
-                if (G < 4) bf_dmma(c[1][a][0], c[1][a][1], a01.y, bb[a]);
-                if (G < 6) bf_dmma(c[2][a][0], c[2][a][1], a23.x, bb[a]);
-                bf_dmma(c[3][a][0], c[3][a][1], a23.y, bb[a]);
+                bf_dmma(c[0][a][0], c[0][a][1], ring[r][0].x, bb[a]);
+                bf_dmma(c[1][a][0], c[1][a][1], ring[r][0].y, bb[a]);
+                bf_dmma(c[2][a][0], c[2][a][1], ring[r][1].x, bb[a]);
+                bf_dmma(c[3][a][0], c[3][a][1], ring[r][1].y, bb[a]);
             }
         }
-        if (gg + 2 < 8) {
-            A0[0] = N0[0]; A0[1] = N0[1];
-            A1[0] = N1[0]; A1[1] = N1[1];
+    }
+    // diagonal block: group gg touches columns 4gg..4gg+3 of the block; atom t (rows 8t..8t+7) is
+    // non-zero only for gg < 2t + 2.
+#pragma unroll
+    for (int gg = 0; gg < 8; ++gg) {
+        const int g = ng_full + gg;
+        if (gg + R - 1 < 8) {
+            ring[(gg + R - 1) % R][0] = __ldg(Ap + (size_t)(g + R - 1) * 64);
+            ring[(gg + R - 1) % R][1] = __ldg(Ap + (size_t)(g + R - 1) * 64 + 32);
+        }
+        double bb[NA];
+#pragma unroll
+        for (int a = 0; a < NA; ++a) bb[a] = Bp[(size_t)g * gstride + a * 32];
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+            if (gg < 2) bf_dmma(c[0][a][0], c[0][a][1], ring[gg % R][0].x, bb[a]);
+            if (gg < 4) bf_dmma(c[1][a][0], c[1][a][1], ring[gg % R][0].y, bb[a]);
+            if (gg < 6) bf_dmma(c[2][a][0], c[2][a][1], ring[gg % R][1].x, bb[a]);
+            bf_dmma(c[3][a][0], c[3][a][1], ring[gg % R][1].y, bb[a]);
         }
     }
 #pragma unroll
@@ -185,10 +194,10 @@ __device__ __forceinline__ void mma_block(const double* __restrict__ Aset, const
 // Work units = (row-block pair) x (column slice of NA atoms); warps take units round-robin.  Unit
 // u: slice = u % nslices, pair = u / nslices.  Each warp owns one slice for the whole phase so its
 // column sums stay in registers; warps beyond the unit count idle.
-template <int NA, int MINB>
-__device__ __noinline__ void mma_phase(int nb, int NTA, const double* __restrict__ Aset,
-                                       const double* __restrict__ Bt, double* __restrict__ spart) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+template <int NA, int R>
+__device__ __forceinline__ void mma_phase_body(int nb, int NTA, const double* __restrict__ Aset,
+                                       const double* __restrict__ Bt, double* __restrict__ spart, int warp) {
+    const int lane = threadIdx.x & 31;
     const int NT = 8 * NTA;
     const int nslices = NTA / NA;
     const int nq = BF_WARPS / nslices;            // pair queues per slice
@@ -201,8 +210,8 @@ __device__ __noinline__ void mma_phase(int nb, int NTA, const double* __restrict
     for (int a = 0; a < NA; ++a) cs[a][0] = cs[a][1] = 0.0;
     for (int pr = wq; pr < npairs; pr += nq) {
         const int b_hi = nb - 1 - pr;
-        mma_block<NA>(Aset, Bt, NTA, a0, b_hi, cs);
-        if (pr != b_hi) mma_block<NA>(Aset, Bt, NTA, a0, pr, cs);
+        mma_block<NA, R>(Aset, Bt, NTA, a0, b_hi, cs);
+        if (pr != b_hi) mma_block<NA, R>(Aset, Bt, NTA, a0, pr, cs);
     }
     // column c = 8 (a0 + a) + 2 (lane & 3) + q; reduce over the 8 row lanes (lane >> 2)
 #pragma unroll
@@ -217,6 +226,13 @@ __device__ __noinline__ void mma_phase(int nb, int NTA, const double* __restrict
         }
 }
 
+// single-buffer kernel: out-of-line copy per register budget
+template <int NA, int MINB>
+__device__ __noinline__ void mma_phase(int nb, int NTA, const double* __restrict__ Aset,
+                                       const double* __restrict__ Bt, double* __restrict__ spart, int warp) {
+    mma_phase_body<NA, 4>(nb, NTA, Aset, Bt, spart, warp);
+}
+
 template <int D, int NTA, int MINB>
 __global__ void __launch_bounds__(BF_THREADS, MINB) bf_posterior_kernel(PostParams p) {
     constexpr int NT = 8 * NTA;
@@ -227,6 +243,7 @@ __global__ void __launch_bounds__(BF_THREADS, MINB) bf_posterior_kernel(PostPara
     double* mpart = xs_s + dd * NT;                      // BF_WARPS * NT
     double* spart = mpart + BF_WARPS * NT;               // BF_WARPS * NT
     double* w_s = spart + BF_WARPS * NT;                 // BF_MAX_DIM
+    double* tab_s = w_s + BF_MAX_DIM;                    // BF_EXP_TAB_N
     __shared__ BfBest red_best[4][2];
     __shared__ BfTop2 red_top[2];
 
@@ -242,9 +259,10 @@ __global__ void __launch_bounds__(BF_THREADS, MINB) bf_posterior_kernel(PostPara
     }
     for (int e = threadIdx.x; e < BF_WARPS * NT; e += BF_THREADS) spart[e] = 0.0;
     if (threadIdx.x < dd) w_s[threadIdx.x] = p.inv_l2[(size_t)hp * dd + threadIdx.x];
+    if (threadIdx.x < BF_EXP_TAB_N) tab_s[threadIdx.x] = bf_exp_tab_g[threadIdx.x];
     __syncthreads();
 
-    gen_tile<D, NTA>(p, w_s, xs_s, Bt, mpart, p.alpha + (size_t)set * p.n, amp);
+    gen_tile<D, NTA>(p, w_s, xs_s, Bt, mpart, p.alpha + (size_t)set * p.n, amp, tab_s, threadIdx.x >> 5);
     __syncthreads();
 
     const double* Aset = p.linv + (size_t)set * p.linv_stride;
@@ -255,10 +273,10 @@ __global__ void __launch_bounds__(BF_THREADS, MINB) bf_posterior_kernel(PostPara
         for (int cand = (MINB == 2 && NTA > 4) ? NTA / 2 : NTA; cand >= 1; --cand)   // 128-register budget
             if (NTA % cand == 0 && (cand == 1 || BF_WARPS / (NTA / cand) <= npairs)) { NA = cand; break; }
         switch (NA) {
-            case 6: if (NTA == 6 && MINB == 1) mma_phase<6, MINB>(p.nb, NTA, Aset, Bt, spart); break;
-            case 3: if (NTA % 3 == 0) mma_phase<3, MINB>(p.nb, NTA, Aset, Bt, spart); break;
-            case 2: if (NTA % 2 == 0) mma_phase<2, MINB>(p.nb, NTA, Aset, Bt, spart); break;
-            default: mma_phase<1, MINB>(p.nb, NTA, Aset, Bt, spart); break;
+            case 6: if (NTA == 6 && MINB == 1) mma_phase<6, MINB>(p.nb, NTA, Aset, Bt, spart, threadIdx.x >> 5); break;
+            case 3: if (NTA % 3 == 0) mma_phase<3, MINB>(p.nb, NTA, Aset, Bt, spart, threadIdx.x >> 5); break;
+            case 2: if (NTA % 2 == 0) mma_phase<2, MINB>(p.nb, NTA, Aset, Bt, spart, threadIdx.x >> 5); break;
+            default: mma_phase<1, MINB>(p.nb, NTA, Aset, Bt, spart, threadIdx.x >> 5); break;
         }
     }
     __syncthreads();
@@ -331,6 +349,186 @@ __global__ void __launch_bounds__(BF_THREADS, MINB) bf_posterior_kernel(PostPara
     }
 }
 
+// ---- pipelined variant (the one used whenever two B tiles fit in shared memory) ---------------
+// One CTA per SM, 16 warps, a chunk of consecutive tiles of one set.
+//   warps 0-7   consumers: phase B back to back on buffer i & 1;
+//   warps 8-14  generators: phase A of tile i + 1 into the other buffer while tile i is multiplied;
+//   warp  15    finisher: phase C of tile i as soon as its column sums are complete.
+// so the shared FP64/DMMA pipe never waits for a phase change.  Hand-off through named barriers:
+//   FULL[b]  generators + finisher arrive, consumers wait   (B tile / mean partials of buffer b ready;
+//            the finisher's arrival also says it has finished reading the column sums of tile i - 2)
+//   DONE[b]  consumers arrive, generators + finisher wait   (B tile b free, column sums of b ready)
+//   GEN      generators only (candidate coordinates staged in shared memory)
+// The mean partials are triple-buffered: tile t + 3 is generated only after DONE of tile t + 1, at
+// which the finisher arrives after it has finished tile t.
+#define BF_BAR_FULL 1
+#define BF_BAR_DONE 3
+#define BF_BAR_GEN 5
+#define BF_PIPE_THREADS (2 * BF_THREADS)
+#define BF_GEN_WARPS (BF_WARPS - 1)
+
+__device__ __forceinline__ void bf_bar_sync(int id, int n) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void bf_bar_arrive(int id, int n) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+template <int NTA>
+__device__ __forceinline__ void consumer_mma(int nb, const double* __restrict__ Aset,
+                                             const double* __restrict__ Bt, double* __restrict__ spart, int warp) {
+    // widest column slice (a divisor of NTA, at most 3 atoms: 128-register budget) that still gives
+    // every pair queue a row-block pair
+    const int npairs = (nb + 1) >> 1;
+    int NA = 1;
+    for (int cand = NTA > 4 ? NTA / 2 : NTA; cand >= 1; --cand)
+        if (NTA % cand == 0 && (cand == 1 || BF_WARPS / (NTA / cand) <= npairs)) { NA = cand; break; }
+    switch (NA) {
+        case 3: if (NTA % 3 == 0) mma_phase_body<3, 8>(nb, NTA, Aset, Bt, spart, warp); break;
+        case 2: if (NTA % 2 == 0) mma_phase_body<2, 8>(nb, NTA, Aset, Bt, spart, warp); break;
+        default: mma_phase_body<1, 8>(nb, NTA, Aset, Bt, spart, warp); break;
+    }
+}
+
+template <int D, int NTA>
+__global__ void __launch_bounds__(BF_PIPE_THREADS, 1) bf_posterior_pipe_kernel(PostParams p) {
+    constexpr int NT = 8 * NTA;
+    extern __shared__ __align__(16) double smem[];
+    const int dd = D ? D : p.d;
+    const size_t bt_sz = (size_t)p.np * NT;
+    double* Bt = smem;                                   // 2 x np * NT
+    double* xs_s = Bt + 2 * bt_sz;                       // 2 x d * NT
+    double* mpart = xs_s + 2 * dd * NT;                  // 3 x BF_WARPS * NT
+    double* spart = mpart + 3 * BF_WARPS * NT;           // 2 x BF_WARPS * NT
+    double* w_s = spart + 2 * BF_WARPS * NT;             // BF_MAX_DIM
+    double* tab_s = w_s + BF_MAX_DIM;                    // BF_EXP_TAB_N
+
+    const int set = blockIdx.y;
+    const int hp = p.set_hp ? p.set_hp[set] : set;
+    const long long t0 = (long long)blockIdx.x * p.tpc;
+    long long t1 = t0 + p.tpc;
+    if (t1 > p.ntiles) t1 = p.ntiles;
+    const int T = (int)(t1 - t0);                        // >= 1 by construction of the grid
+    const double amp = p.amp[hp];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int e = threadIdx.x; e < 2 * BF_WARPS * NT; e += BF_PIPE_THREADS) spart[e] = 0.0;
+    for (int e = threadIdx.x; e < 3 * BF_WARPS * NT; e += BF_PIPE_THREADS) mpart[e] = 0.0;
+    if (threadIdx.x < dd) w_s[threadIdx.x] = p.inv_l2[(size_t)hp * dd + threadIdx.x];
+    if (threadIdx.x < BF_EXP_TAB_N) tab_s[threadIdx.x] = bf_exp_tab_g[threadIdx.x];
+    __syncthreads();
+
+    // Register hand-over (warpgroup-wide): the DMMA warps need the accumulators plus an 8-deep
+    // operand ring (~150 registers); the other warps need far fewer.  (152 + 104) * 256 = 64 K.
+    if (warp < BF_WARPS) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        // ---------------- consumers: phase B ----------------
+        const double* Aset = p.linv + (size_t)set * p.linv_stride;
+        for (int i = 0; i < T; ++i) {
+            const int b = i & 1;
+            bf_bar_sync(BF_BAR_FULL + b, BF_PIPE_THREADS);
+            if (!(p.debug_skip & 1)) consumer_mma<NTA>(p.nb, Aset, Bt + b * bt_sz, spart + b * BF_WARPS * NT, warp);
+            __threadfence_block();
+            bf_bar_arrive(BF_BAR_DONE + b, BF_PIPE_THREADS);
+        }
+        return;
+    }
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    const int pw = warp - BF_WARPS;
+
+    if (pw < BF_GEN_WARPS) {
+        // ---------------- generators: phase A ----------------
+        const int gtid = threadIdx.x - BF_THREADS;
+        const double* alpha = p.alpha + (size_t)set * p.n;
+        for (int t = 0; t < T; ++t) {
+            const int b = t & 1;
+            if (t >= 2) bf_bar_sync(BF_BAR_DONE + b, BF_PIPE_THREADS);     // tile t - 2 left buffer b
+            const long long c_base = (t0 + t) * NT;
+            double* xs_b = xs_s + b * dd * NT;
+            for (int e = gtid; e < dd * NT; e += BF_GEN_WARPS * 32) {
+                const int a = e / NT, c = e - a * NT;
+                const long long gi = c_base + c;
+                xs_b[e] = gi < p.N ? p.Xs[gi * dd + a] : 0.0;
+            }
+            bf_bar_sync(BF_BAR_GEN, BF_GEN_WARPS * 32);
+            if (!(p.debug_skip & 2))
+                gen_tile<D, NTA>(p, w_s, xs_b, Bt + b * bt_sz, mpart + (t % 3) * BF_WARPS * NT, alpha, amp, tab_s, pw,
+                                 BF_GEN_WARPS);
+            __threadfence_block();
+            bf_bar_arrive(BF_BAR_FULL + b, BF_PIPE_THREADS);
+        }
+        // DONE barriers the generators did not wait on still count them
+        for (int t = (T >= 2 ? T - 2 : 0); t < T; ++t) bf_bar_sync(BF_BAR_DONE + (t & 1), BF_PIPE_THREADS);
+        return;
+    }
+
+    // ---------------- finisher: phase C ----------------
+    const double sc = p.scale ? p.scale[set] : 1.0;
+    const double sh = p.shift ? p.shift[set] : 0.0;
+    BfBest best[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) best[k] = bf_best_init();
+    BfTop2 top = bf_top2_init();
+    bf_bar_arrive(BF_BAR_FULL + 0, BF_PIPE_THREADS);                 // tiles 0 and 1 need nothing from here
+    if (T > 1) bf_bar_arrive(BF_BAR_FULL + 1, BF_PIPE_THREADS);
+    for (int i = 0; i < T; ++i) {
+        const int b = i & 1;
+        bf_bar_sync(BF_BAR_DONE + b, BF_PIPE_THREADS);
+        const double* mp = mpart + (i % 3) * BF_WARPS * NT;
+        const double* sp = spart + b * BF_WARPS * NT;
+#pragma unroll
+        for (int c = lane; c < NT; c += 32) {
+            const long long gi = (t0 + i) * NT + c;
+            if (gi < p.N && !(p.debug_skip & 4)) {
+                double mean = 0.0, s = 0.0;
+#pragma unroll
+                for (int w = 0; w < BF_WARPS; ++w) mean += mp[w * NT + c];
+#pragma unroll
+                for (int w = 0; w < BF_WARPS; ++w) s += sp[w * NT + c];
+                const double mu = mean * sc + sh;
+                const double var = (amp - s) * (sc * sc);
+                if (p.mu_out) p.mu_out[(size_t)set * p.N + gi] = mu;
+                if (p.var_out) p.var_out[(size_t)set * p.N + gi] = var;
+                if (p.acq_mask) {
+                    const double spread = p.spread_is_sqrt ? sqrt(var) : var;
+                    if (p.acq_mask & BF_ACQ_EI)
+                        bf_best_take(best[BF_SLOT_EI],
+                                     (mu - p.curr_max - p.xi) * bf_norm_pdf(mu) + var * bf_norm_cdf(mu), gi);
+                    if (p.acq_mask & BF_ACQ_PI)
+                        bf_best_take(best[BF_SLOT_PI], bf_norm_cdf((mu - p.curr_max - p.xi) / spread), gi);
+                    if (p.acq_mask & BF_ACQ_UCB) bf_best_take(best[BF_SLOT_UCB], mu + p.kt * spread, gi);
+                    if (p.acq_mask & BF_ACQ_GREEDY) bf_top2_merge(top, mu, gi, -INFINITY);
+                }
+            }
+        }
+        __threadfence_block();
+        if (i + 2 < T) bf_bar_arrive(BF_BAR_FULL + b, BF_PIPE_THREADS);   // column sums of tile i consumed
+    }
+    if (p.acq_mask) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) best[k] = bf_best_warp(best[k]);
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            const double t1v = __shfl_xor_sync(0xffffffffu, top.t1, m);
+            const long long i1 = __shfl_xor_sync(0xffffffffu, top.i1, m);
+            const double t2 = __shfl_xor_sync(0xffffffffu, top.t2, m);
+            bf_top2_merge(top, t1v, i1, t2);
+        }
+        if (lane == 0) {
+            double* pv = p.part_val + ((size_t)set * p.tiles + blockIdx.x) * BF_NSLOT_VAL;
+            long long* pi = p.part_idx + ((size_t)set * p.tiles + blockIdx.x) * BF_NSLOT_IDX;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                pv[k] = best[k].v;
+                pi[k] = best[k].i;
+            }
+            pv[BF_SLOT_GREEDY] = top.t1;
+            pi[BF_SLOT_GREEDY] = top.i1;
+            pv[BF_SLOT_TOP2] = top.t2;
+        }
+    }
+}
+
 // ---- per-set reduction of the tile partials --------------------------------------------------
 __global__ void bf_acq_finalize_kernel(int tiles, const double* __restrict__ part_val,
                                        const long long* __restrict__ part_idx,
@@ -383,7 +581,7 @@ __global__ void bf_acq_finalize_kernel(int tiles, const double* __restrict__ par
 
 // ---- host side ------------------------------------------------------------------------------
 static size_t posterior_smem_bytes(int np, int NT, int d) {
-    return sizeof(double) * ((size_t)np * NT + (size_t)d * NT + 2 * (size_t)BF_WARPS * NT + BF_MAX_DIM);
+    return sizeof(double) * ((size_t)np * NT + (size_t)d * NT + 2 * (size_t)BF_WARPS * NT + BF_MAX_DIM + BF_EXP_TAB_N);
 }
 
 extern "C" int bf_padded_n(int n) { return (n + 31) & ~31; }
@@ -393,24 +591,49 @@ extern "C" size_t bf_linv_packed_doubles(int n) {
     return bf_linv_block_off(nb);
 }
 
-// Tile choice.  Preference: two CTAs per SM (the phases of one tile overlap the DMMA phase of the
-// other) with the widest tile that fits, then one CTA per SM.
-struct TileChoice { int NT; int minb; };
+// Tile / launch choice.  Pipelined kernel (two B tiles in shared memory, one 16-warp CTA per SM)
+// whenever it fits; otherwise the single-buffer kernel with one CTA per SM.
+struct TileChoice { int NT; int pipe; };
+static size_t posterior_pipe_smem_bytes(int np, int NT, int d) {
+    return sizeof(double) * (2 * ((size_t)np * NT + (size_t)d * NT) + 5 * (size_t)BF_WARPS * NT + BF_MAX_DIM + BF_EXP_TAB_N);
+}
 static TileChoice choose_tile(int n) {
     const int np = bf_padded_n(n);
-    const size_t two = (size_t)(233472 / 2 - 1024 - 256), one = (size_t)227 * 1024 - 256;
-    const TileChoice pref[5] = {{48, 2}, {24, 2}, {48, 1}, {24, 1}, {16, 1}};
-    for (int i = 0; i < 5; ++i)
-        if (posterior_smem_bytes(np, pref[i].NT, BF_MAX_DIM) <= (pref[i].minb == 2 ? two : one)) return pref[i];
+    const size_t cap = (size_t)227 * 1024 - 256;
+    const int pipe_nt[3] = {48, 24, 16};
+    for (int i = 0; i < 3; ++i)
+        if (posterior_pipe_smem_bytes(np, pipe_nt[i], BF_MAX_DIM) <= cap) return TileChoice{pipe_nt[i], 1};
+    const int one_nt[2] = {24, 16};
+    for (int i = 0; i < 2; ++i)
+        if (posterior_smem_bytes(np, one_nt[i], BF_MAX_DIM) <= cap) return TileChoice{one_nt[i], 0};
     return TileChoice{0, 0};
 }
 
 extern "C" int bf_posterior_tile(int n) { return choose_tile(n).NT; }
 
-extern "C" int bf_posterior_tiles(int n, long long N) {
-    int NT = bf_posterior_tile(n);
-    if (NT == 0 || N <= 0) return 0;
-    return (int)((N + NT - 1) / NT);
+// Partial-result slots (= CTAs) per set.  The pipelined kernel gives each CTA a chunk of
+// consecutive tiles: about 8 CTAs per SM over the whole launch, at least 8 tiles per chunk.
+static void posterior_chunks(int n, long long N, int S, long long* ntiles, int* tpc, int* parts) {
+    const TileChoice tc = choose_tile(n);
+    *ntiles = 0; *tpc = 1; *parts = 0;
+    if (tc.NT == 0 || N <= 0) return;
+    const long long nt = (N + tc.NT - 1) / tc.NT;
+    *ntiles = nt;
+    if (!tc.pipe) { *parts = (int)nt; return; }
+    const long long sets = S > 0 ? S : 1;
+    long long want = (148LL * 8 + sets - 1) / sets;    // CTAs per set
+    if (want < 1) want = 1;
+    long long per = (nt + want - 1) / want;
+    if (per < 8) per = 8;
+    if (per > nt) per = nt;
+    *tpc = (int)per;
+    *parts = (int)((nt + per - 1) / per);
+}
+
+extern "C" int bf_posterior_parts(int n, long long N, int S) {
+    long long nt; int tpc, parts;
+    posterior_chunks(n, N, S, &nt, &tpc, &parts);
+    return parts;
 }
 
 template <int D, int NTA, int MINB>
@@ -426,11 +649,26 @@ static int launch_posterior(const PostParams& p, dim3 grid, size_t smem, cudaStr
     return 0;
 }
 
+template <int D, int NTA>
+static int launch_posterior_pipe(const PostParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(bf_posterior_pipe_kernel<D, NTA>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        bf_set_error("bf_gp_posterior: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+        return (int)e;
+    }
+    bf_posterior_pipe_kernel<D, NTA><<<grid, BF_PIPE_THREADS, smem, st>>>(p);
+    BF_CHECK_LAUNCH("bf_gp_posterior");
+    return 0;
+}
+
 template <int D>
-static int launch_posterior_tile(const PostParams& p, int minb, dim3 grid, size_t smem, cudaStream_t st) {
-    if (p.NT == 48 && minb == 2) return launch_posterior<D, 6, 2>(p, grid, smem, st);
-    if (p.NT == 24 && minb == 2) return launch_posterior<D, 3, 2>(p, grid, smem, st);
-    if (p.NT == 48) return launch_posterior<D, 6, 1>(p, grid, smem, st);
+static int launch_posterior_tile(const PostParams& p, int pipe, dim3 grid, size_t smem, cudaStream_t st) {
+    if (pipe) {
+        if (p.NT == 48) return launch_posterior_pipe<D, 6>(p, grid, smem, st);
+        if (p.NT == 24) return launch_posterior_pipe<D, 3>(p, grid, smem, st);
+        return launch_posterior_pipe<D, 2>(p, grid, smem, st);
+    }
     if (p.NT == 24) return launch_posterior<D, 3, 1>(p, grid, smem, st);
     return launch_posterior<D, 2, 1>(p, grid, smem, st);
 }
@@ -462,16 +700,20 @@ extern "C" int bf_gp_posterior(int kern, long long N, int n, int d, int S, const
     p.acq_mask = acq_mask; p.spread_is_sqrt = spread_is_sqrt;
     p.curr_max = curr_max; p.xi = xi; p.kt = kt;
     p.part_val = part_val; p.part_idx = part_idx;
-    p.tiles = bf_posterior_tiles(n, N);
+    posterior_chunks(n, N, S, &p.ntiles, &p.tpc, &p.tiles);
+    {
+        const char* dbg = getenv("BF_DEBUG_SKIP");
+        p.debug_skip = dbg ? atoi(dbg) : 0;
+    }
     BF_CHECK_ARG(S <= 65535, BF_ERR_SIZE, "bf_gp_posterior: at most 65535 sets per call (got %d)", S);
     dim3 grid(p.tiles, S);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = posterior_smem_bytes(p.np, p.NT, d);
+    const size_t smem = tc.pipe ? posterior_pipe_smem_bytes(p.np, p.NT, d) : posterior_smem_bytes(p.np, p.NT, d);
     switch (d) {
-#define BF_CASE(DD) case DD: return launch_posterior_tile<DD>(p, tc.minb, grid, smem, st);
+#define BF_CASE(DD) case DD: return launch_posterior_tile<DD>(p, tc.pipe, grid, smem, st);
         BF_CASE(1) BF_CASE(2) BF_CASE(3) BF_CASE(4) BF_CASE(5) BF_CASE(6) BF_CASE(7) BF_CASE(8)
 #undef BF_CASE
-        default: return launch_posterior_tile<0>(p, tc.minb, grid, smem, st);   // nDim 9..16 at run time
+        default: return launch_posterior_tile<0>(p, tc.pipe, grid, smem, st);   // nDim 9..16 at run time
     }
     return BF_ERR_SIZE;
 }

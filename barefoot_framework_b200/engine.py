@@ -144,17 +144,18 @@ def posterior_sweep(f, Xs, scale=None, shift=None, want_mu=False, want_var=False
         out.mu = torch.empty((S, N), dtype=F64, device=dev)
     if want_var:
         out.var = torch.empty((S, N), dtype=F64, device=dev)
-    tiles = lib.bf_posterior_tiles(f.n, N)
-    pv = pi = None
     if acq_mask:
-        pv = torch.empty((S, tiles, NSLOT_VAL), dtype=F64, device=dev)
-        pi = torch.empty((S, tiles, NSLOT_IDX), dtype=torch.int64, device=dev)
         out.best_val = torch.empty((S, NSLOT_VAL), dtype=F64, device=dev)
         out.best_idx = torch.empty((S, NSLOT_IDX), dtype=torch.int64, device=dev)
     st = stream()
     for s0 in range(0, S, 65535):
         sc = min(65535, S - s0)
         sl = slice(s0, s0 + sc)
+        pv = pi = None
+        if acq_mask:
+            parts = lib.bf_posterior_parts(f.n, N, sc)
+            pv = torch.empty((sc, parts, NSLOT_VAL), dtype=F64, device=dev)
+            pi = torch.empty((sc, parts, NSLOT_IDX), dtype=torch.int64, device=dev)
         hp_p = None if f.set_hp is None else f.set_hp[s0:].data_ptr()
         inv_p = f.inv_l2 if f.set_hp is not None else f.inv_l2[s0:]
         amp_p = f.amp if f.set_hp is not None else f.amp[s0:]
@@ -168,12 +169,12 @@ def posterior_sweep(f, Xs, scale=None, shift=None, want_mu=False, want_var=False
              None if out.mu is None else out.mu[s0:].data_ptr(),
              None if out.var is None else out.var[s0:].data_ptr(),
              acq_mask, int(bool(spread_is_sqrt)), float(curr_max), float(xi), float(kt),
-             None if pv is None else pv[sl].data_ptr(), None if pi is None else pi[sl].data_ptr(), st)
+             ptr(pv), ptr(pi), st)
         if posterior_events is not None:
             ev1.record()
             posterior_events.append((ev0, ev1))
         if acq_mask:
-            call("bf_acq_finalize", sc, tiles, acq_mask, pv[sl].data_ptr(), pi[sl].data_ptr(),
+            call("bf_acq_finalize", sc, parts, acq_mask, ptr(pv), ptr(pi),
                  out.best_val[sl].data_ptr(), out.best_idx[sl].data_ptr(), st)
     return out
 

@@ -63,7 +63,8 @@ const char* bf_last_error(void);
 int    bf_padded_n(int n);                 /* np: n rounded up to 32 */
 size_t bf_linv_packed_doubles(int n);      /* doubles per set of the packed L^-1 operand */
 int    bf_posterior_tile(int n);           /* candidates per CTA chosen for this n (0: too large) */
-int    bf_posterior_tiles(int n, long long N); /* CTAs per set = ceil(N / tile) */
+int    bf_posterior_parts(int n, long long N, int S); /* partial-result slots (CTAs) per set of a
+                                                          bf_gp_posterior call over S sets */
 
 /* ---- (1)+(2) setup of a GP: gpModel.py:17-42 (george GP.compute) --------------------------- */
 /* K[s] = amp * k(X, X; inv_l2) + diag((sqrt(yerr^2 + 1.25e-12))^2), written as an np x np
@@ -91,7 +92,8 @@ int bf_factor_finish(int n, int S, const double* L, const double* y, long long y
 /* For every set s and candidate c: k* = amp k(x*_c, X); mu = k*.alpha; var = amp - |L^-1 k*|^2;
  * mu' = mu * scale[s] + shift[s]; var' = var * scale[s]^2 (scale/shift may be NULL = 1/0).
  * mu_out / var_out ([S x N]) are optional.  If acq_mask != 0 the per-tile partial maxima are
- * written to part_val [S x tiles x 5] / part_idx [S x tiles x 4]; reduce with bf_acq_finalize.
+ * written to part_val [S x parts x 5] / part_idx [S x parts x 4], parts = bf_posterior_parts(n, N, S);
+ * reduce with bf_acq_finalize(S, parts, ...).
  * spread_is_sqrt: PI/UCB receive sqrt(var') (ROM stage, util.py:451,519) instead of var'
  * (TM/batch stage, util.py:598-612).  EI always receives var' (util.py:323-326). */
 int bf_gp_posterior(int kern, long long N, int n, int d, int S,

@@ -35,7 +35,8 @@ def test_library_exports_every_symbol():
     nb = 16
     assert lib.bf_linv_packed_doubles(500) == 1024 * nb * (nb + 1) // 2
     assert lib.bf_posterior_tile(500) == 24
-    assert lib.bf_posterior_tiles(500, 10 ** 6) == (10 ** 6 + 23) // 24
+    assert 148 <= lib.bf_posterior_parts(500, 10 ** 6, 1) <= (10 ** 6 + 23) // 24
+    assert lib.bf_posterior_parts(500, 10 ** 5, 1000) >= 1
     assert lib.bf_posterior_tile(5000) == 0
 
 

@@ -1,0 +1,2 @@
+for m in 0 1 2 4 3 6; do BF_DEBUG_SKIP=$m timeout 100 python bench.py --steps 5 --warmup 3 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('skip=$m kernel_ms', d['roofline']['kernel_ms'])"; done
