@@ -4,20 +4,17 @@
 // probability_improvement / upper_conf_bound / greedy (acquisitionFunc.py:98-214,
 // util.py:655-665) for all hyper-parameter sets x all candidates in one launch.
 //
-// One CTA = one tile of NT = 8 NTA candidates of one set.  The tile is sized so that TWO CTAs fit on
-// an SM whenever possible (NT = 24 at n = 500): FP64 DMMA and FP64 FMA share one SM pipe, so the only
-// way to keep it busy during the FP64-only phases A and C of one tile is the DMMA phase of another.
-// Phases:
+// One tile = NT = 8 NTA candidates of one set (NT = 24 at n = 500).  Phases per tile:
 //   phase A  cross-covariance tile k*[np x NT] generated straight into shared memory in the
 //            DMMA B-fragment layout (never touches HBM); mean = k* . alpha folded in.
 //   phase B  V = L^-1 k* on the FP64 tensor cores (mma.sync m8n8k4 -> DMMA.8x8x4).  L^-1 is
-//            block lower triangular in a pre-packed fragment layout streamed from L2 with
-//            register double-buffering; warps own balanced (b, nb-1-b) row-block pairs.
+//            block lower triangular in a pre-packed fragment layout streamed from L2 through a
+//            register ring; warps own balanced (b, nb-1-b) row-block pairs.
 //            Only the column sums of V^2 are kept.
-//   phase C  var = amp - |V|^2, de-normalise, acquisition values, per-tile (max, first index)
+//   phase C  var = amp - |V|^2, de-normalise, acquisition values, running (max, first index)
 //            and top-2 of the mean.
-#include <stdlib.h>
-
+// Two kernels: bf_posterior_dual_kernel (two tiles per CTA in lock step, used whenever two B tiles
+// fit in shared memory) and bf_posterior_kernel (one tile per CTA, larger n).
 #include "bf_common.cuh"
 
 struct PostParams {
@@ -34,7 +31,6 @@ struct PostParams {
     int tiles;            // partial slots per set (= CTAs per set)
     int tpc;              // tiles per CTA
     long long ntiles;     // candidate tiles per set
-    int debug_skip;       // profiling only (BF_DEBUG_SKIP): 1 = no phase B, 2 = no phase A, 4 = no phase C
 };
 
 // ---- phase A ------------------------------------------------------------------------------
@@ -61,7 +57,7 @@ __device__ __forceinline__ void gen_tile(const PostParams& p, const double* __re
 
     // G k-groups per trip: G * NTA independent (branch-free) evaluation chains per lane hide the
     // latency of the FP64 pipe, which these warps share with the DMMA warps
-    constexpr int G = (NTA <= 3 && DR <= 8) ? 2 : 1;
+    constexpr int G = 1;
     const int ng = p.np >> 2;
     for (int g0 = warp; g0 < ng; g0 += G * nwarps) {
         double xj[G][DR], aj[G];
@@ -349,34 +345,21 @@ __global__ void __launch_bounds__(BF_THREADS, MINB) bf_posterior_kernel(PostPara
     }
 }
 
-// ---- pipelined variant (the one used whenever two B tiles fit in shared memory) ---------------
-// One CTA per SM, 16 warps, a chunk of consecutive tiles of one set.
-//   warps 0-7   consumers: phase B back to back on buffer i & 1;
-//   warps 8-14  generators: phase A of tile i + 1 into the other buffer while tile i is multiplied;
-//   warp  15    finisher: phase C of tile i as soon as its column sums are complete.
-// so the shared FP64/DMMA pipe never waits for a phase change.  Hand-off through named barriers:
-//   FULL[b]  generators + finisher arrive, consumers wait   (B tile / mean partials of buffer b ready;
-//            the finisher's arrival also says it has finished reading the column sums of tile i - 2)
-//   DONE[b]  consumers arrive, generators + finisher wait   (B tile b free, column sums of b ready)
-//   GEN      generators only (candidate coordinates staged in shared memory)
-// The mean partials are triple-buffered: tile t + 3 is generated only after DONE of tile t + 1, at
-// which the finisher arrives after it has finished tile t.
-#define BF_BAR_FULL 1
-#define BF_BAR_DONE 3
-#define BF_BAR_GEN 5
-#define BF_PIPE_THREADS (2 * BF_THREADS)
-#define BF_GEN_WARPS (BF_WARPS - 1)
-
-__device__ __forceinline__ void bf_bar_sync(int id, int n) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
-}
-__device__ __forceinline__ void bf_bar_arrive(int id, int n) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
-}
+// ---- dual-tile variant (the one used whenever two B tiles fit in shared memory) ---------------
+// Measured on B200 (tools/dmma_probe.cu, profiles/): FP64 FMA and DMMA share one SM pipe, and an FP64
+// instruction issued between DMMAs costs about three times its nominal pipe time, so overlapping the
+// generator of one tile with the DMMA phase of another (two CTAs per SM, or warp-specialised
+// producer/consumer warps) loses more than it hides.  This kernel therefore keeps the phases
+// separate SM-wide: one CTA per SM, 16 warps in two groups of 8; each group owns one candidate tile
+// and one shared-memory buffer, and all 16 warps move through phase A, phase B and phase C in
+// lock step.  Phase A then runs at the full FP64 rate with 16 warps of branch-free evaluation
+// chains, and phase B has 4 DMMA warps per scheduler to cover the L2 latency of the L^-1 stream.
+// A CTA walks a chunk of consecutive tile pairs and keeps its running maxima in registers.
+#define BF_DUAL_THREADS (2 * BF_THREADS)
 
 template <int NTA>
-__device__ __forceinline__ void consumer_mma(int nb, const double* __restrict__ Aset,
-                                             const double* __restrict__ Bt, double* __restrict__ spart, int warp) {
+__device__ __forceinline__ void dual_mma(int nb, const double* __restrict__ Aset, const double* __restrict__ Bt,
+                                         double* __restrict__ spart, int warp) {
     // widest column slice (a divisor of NTA, at most 3 atoms: 128-register budget) that still gives
     // every pair queue a row-block pair
     const int npairs = (nb + 1) >> 1;
@@ -384,127 +367,95 @@ __device__ __forceinline__ void consumer_mma(int nb, const double* __restrict__ 
     for (int cand = NTA > 4 ? NTA / 2 : NTA; cand >= 1; --cand)
         if (NTA % cand == 0 && (cand == 1 || BF_WARPS / (NTA / cand) <= npairs)) { NA = cand; break; }
     switch (NA) {
-        case 3: if (NTA % 3 == 0) mma_phase_body<3, 8>(nb, NTA, Aset, Bt, spart, warp); break;
-        case 2: if (NTA % 2 == 0) mma_phase_body<2, 8>(nb, NTA, Aset, Bt, spart, warp); break;
-        default: mma_phase_body<1, 8>(nb, NTA, Aset, Bt, spart, warp); break;
+        case 3: if (NTA % 3 == 0) mma_phase<3, 2>(nb, NTA, Aset, Bt, spart, warp); break;
+        case 2: if (NTA % 2 == 0) mma_phase<2, 2>(nb, NTA, Aset, Bt, spart, warp); break;
+        default: mma_phase<1, 2>(nb, NTA, Aset, Bt, spart, warp); break;
     }
 }
 
 template <int D, int NTA>
-__global__ void __launch_bounds__(BF_PIPE_THREADS, 1) bf_posterior_pipe_kernel(PostParams p) {
+__global__ void __launch_bounds__(BF_DUAL_THREADS, 1) bf_posterior_dual_kernel(PostParams p) {
     constexpr int NT = 8 * NTA;
     extern __shared__ __align__(16) double smem[];
     const int dd = D ? D : p.d;
     const size_t bt_sz = (size_t)p.np * NT;
-    double* Bt = smem;                                   // 2 x np * NT
-    double* xs_s = Bt + 2 * bt_sz;                       // 2 x d * NT
-    double* mpart = xs_s + 2 * dd * NT;                  // 3 x BF_WARPS * NT
-    double* spart = mpart + 3 * BF_WARPS * NT;           // 2 x BF_WARPS * NT
-    double* w_s = spart + 2 * BF_WARPS * NT;             // BF_MAX_DIM
-    double* tab_s = w_s + BF_MAX_DIM;                    // BF_EXP_TAB_N
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = warp >> 3, gw = warp & 7, gtid = threadIdx.x & (BF_THREADS - 1);
+    double* Bt = smem + grp * bt_sz;                                    // 2 x np * NT
+    double* xs_s = smem + 2 * bt_sz + grp * dd * NT;                    // 2 x d * NT
+    double* mpart = smem + 2 * bt_sz + 2 * dd * NT + grp * BF_WARPS * NT;          // 2 x BF_WARPS * NT
+    double* spart = smem + 2 * bt_sz + 2 * dd * NT + (2 + grp) * BF_WARPS * NT;    // 2 x BF_WARPS * NT
+    double* w_s = smem + 2 * bt_sz + 2 * dd * NT + 4 * BF_WARPS * NT;   // BF_MAX_DIM
+    double* tab_s = w_s + BF_MAX_DIM;                                   // BF_EXP_TAB_N
 
     const int set = blockIdx.y;
     const int hp = p.set_hp ? p.set_hp[set] : set;
     const long long t0 = (long long)blockIdx.x * p.tpc;
     long long t1 = t0 + p.tpc;
     if (t1 > p.ntiles) t1 = p.ntiles;
-    const int T = (int)(t1 - t0);                        // >= 1 by construction of the grid
     const double amp = p.amp[hp];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    for (int e = threadIdx.x; e < 2 * BF_WARPS * NT; e += BF_PIPE_THREADS) spart[e] = 0.0;
-    for (int e = threadIdx.x; e < 3 * BF_WARPS * NT; e += BF_PIPE_THREADS) mpart[e] = 0.0;
-    if (threadIdx.x < dd) w_s[threadIdx.x] = p.inv_l2[(size_t)hp * dd + threadIdx.x];
-    if (threadIdx.x < BF_EXP_TAB_N) tab_s[threadIdx.x] = bf_exp_tab_g[threadIdx.x];
-    __syncthreads();
-
-    // Register hand-over (warpgroup-wide): the DMMA warps need the accumulators plus an 8-deep
-    // operand ring (~150 registers); the other warps need far fewer.  (152 + 104) * 256 = 64 K.
-    if (warp < BF_WARPS) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
-        // ---------------- consumers: phase B ----------------
-        const double* Aset = p.linv + (size_t)set * p.linv_stride;
-        for (int i = 0; i < T; ++i) {
-            const int b = i & 1;
-            bf_bar_sync(BF_BAR_FULL + b, BF_PIPE_THREADS);
-            if (!(p.debug_skip & 1)) consumer_mma<NTA>(p.nb, Aset, Bt + b * bt_sz, spart + b * BF_WARPS * NT, warp);
-            __threadfence_block();
-            bf_bar_arrive(BF_BAR_DONE + b, BF_PIPE_THREADS);
-        }
-        return;
-    }
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-    const int pw = warp - BF_WARPS;
-
-    if (pw < BF_GEN_WARPS) {
-        // ---------------- generators: phase A ----------------
-        const int gtid = threadIdx.x - BF_THREADS;
-        const double* alpha = p.alpha + (size_t)set * p.n;
-        for (int t = 0; t < T; ++t) {
-            const int b = t & 1;
-            if (t >= 2) bf_bar_sync(BF_BAR_DONE + b, BF_PIPE_THREADS);     // tile t - 2 left buffer b
-            const long long c_base = (t0 + t) * NT;
-            double* xs_b = xs_s + b * dd * NT;
-            for (int e = gtid; e < dd * NT; e += BF_GEN_WARPS * 32) {
-                const int a = e / NT, c = e - a * NT;
-                const long long gi = c_base + c;
-                xs_b[e] = gi < p.N ? p.Xs[gi * dd + a] : 0.0;
-            }
-            bf_bar_sync(BF_BAR_GEN, BF_GEN_WARPS * 32);
-            if (!(p.debug_skip & 2))
-                gen_tile<D, NTA>(p, w_s, xs_b, Bt + b * bt_sz, mpart + (t % 3) * BF_WARPS * NT, alpha, amp, tab_s, pw,
-                                 BF_GEN_WARPS);
-            __threadfence_block();
-            bf_bar_arrive(BF_BAR_FULL + b, BF_PIPE_THREADS);
-        }
-        // DONE barriers the generators did not wait on still count them
-        for (int t = (T >= 2 ? T - 2 : 0); t < T; ++t) bf_bar_sync(BF_BAR_DONE + (t & 1), BF_PIPE_THREADS);
-        return;
-    }
-
-    // ---------------- finisher: phase C ----------------
+    const double* alpha = p.alpha + (size_t)set * p.n;
+    const double* Aset = p.linv + (size_t)set * p.linv_stride;
     const double sc = p.scale ? p.scale[set] : 1.0;
     const double sh = p.shift ? p.shift[set] : 0.0;
+
+    for (int e = gtid; e < BF_WARPS * NT; e += BF_THREADS) spart[e] = 0.0;   // idle-queue slots stay 0
+    if (threadIdx.x < dd) w_s[threadIdx.x] = p.inv_l2[(size_t)hp * dd + threadIdx.x];
+    if (threadIdx.x < BF_EXP_TAB_N) tab_s[threadIdx.x] = bf_exp_tab_g[threadIdx.x];
+
     BfBest best[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) best[k] = bf_best_init();
     BfTop2 top = bf_top2_init();
-    bf_bar_arrive(BF_BAR_FULL + 0, BF_PIPE_THREADS);                 // tiles 0 and 1 need nothing from here
-    if (T > 1) bf_bar_arrive(BF_BAR_FULL + 1, BF_PIPE_THREADS);
-    for (int i = 0; i < T; ++i) {
-        const int b = i & 1;
-        bf_bar_sync(BF_BAR_DONE + b, BF_PIPE_THREADS);
-        const double* mp = mpart + (i % 3) * BF_WARPS * NT;
-        const double* sp = spart + b * BF_WARPS * NT;
+
+    for (long long tp = t0; tp < t1; tp += 2) {
+        const long long tile = tp + grp;
+        const bool active = tile < t1;
+        const long long c_base = tile * NT;
+        for (int e = gtid; e < dd * NT; e += BF_THREADS) {
+            const int a = e / NT, c = e - a * NT;
+            const long long gi = c_base + c;
+            xs_s[e] = (active && gi < p.N) ? p.Xs[gi * dd + a] : 0.0;
+        }
+        __syncthreads();     // also orders the previous phase C before mpart / spart are rewritten
+        if (active) gen_tile<D, NTA>(p, w_s, xs_s, Bt, mpart, alpha, amp, tab_s, gw);
+        __syncthreads();
+        if (active) dual_mma<NTA>(p.nb, Aset, Bt, spart, gw);
+        __syncthreads();
+        if (active && gw == 0) {
+            // ---- phase C: one lane per candidate (two rounds when the tile has 48) ----
 #pragma unroll
-        for (int c = lane; c < NT; c += 32) {
-            const long long gi = (t0 + i) * NT + c;
-            if (gi < p.N && !(p.debug_skip & 4)) {
-                double mean = 0.0, s = 0.0;
+            for (int c = lane; c < NT; c += 32) {
+                const long long gi = c_base + c;
+                if (gi < p.N) {
+                    double mean = 0.0, s = 0.0;
 #pragma unroll
-                for (int w = 0; w < BF_WARPS; ++w) mean += mp[w * NT + c];
+                    for (int w = 0; w < BF_WARPS; ++w) mean += mpart[w * NT + c];
 #pragma unroll
-                for (int w = 0; w < BF_WARPS; ++w) s += sp[w * NT + c];
-                const double mu = mean * sc + sh;
-                const double var = (amp - s) * (sc * sc);
-                if (p.mu_out) p.mu_out[(size_t)set * p.N + gi] = mu;
-                if (p.var_out) p.var_out[(size_t)set * p.N + gi] = var;
-                if (p.acq_mask) {
-                    const double spread = p.spread_is_sqrt ? sqrt(var) : var;
-                    if (p.acq_mask & BF_ACQ_EI)
-                        bf_best_take(best[BF_SLOT_EI],
-                                     (mu - p.curr_max - p.xi) * bf_norm_pdf(mu) + var * bf_norm_cdf(mu), gi);
-                    if (p.acq_mask & BF_ACQ_PI)
-                        bf_best_take(best[BF_SLOT_PI], bf_norm_cdf((mu - p.curr_max - p.xi) / spread), gi);
-                    if (p.acq_mask & BF_ACQ_UCB) bf_best_take(best[BF_SLOT_UCB], mu + p.kt * spread, gi);
-                    if (p.acq_mask & BF_ACQ_GREEDY) bf_top2_merge(top, mu, gi, -INFINITY);
+                    for (int w = 0; w < BF_WARPS; ++w) s += spart[w * NT + c];
+                    const double mu = mean * sc + sh;
+                    const double var = (amp - s) * (sc * sc);
+                    if (p.mu_out) p.mu_out[(size_t)set * p.N + gi] = mu;
+                    if (p.var_out) p.var_out[(size_t)set * p.N + gi] = var;
+                    if (p.acq_mask) {
+                        const double spread = p.spread_is_sqrt ? sqrt(var) : var;
+                        if (p.acq_mask & BF_ACQ_EI)
+                            bf_best_take(best[BF_SLOT_EI],
+                                         (mu - p.curr_max - p.xi) * bf_norm_pdf(mu) + var * bf_norm_cdf(mu), gi);
+                        if (p.acq_mask & BF_ACQ_PI)
+                            bf_best_take(best[BF_SLOT_PI], bf_norm_cdf((mu - p.curr_max - p.xi) / spread), gi);
+                        if (p.acq_mask & BF_ACQ_UCB) bf_best_take(best[BF_SLOT_UCB], mu + p.kt * spread, gi);
+                        if (p.acq_mask & BF_ACQ_GREEDY) bf_top2_merge(top, mu, gi, -INFINITY);
+                    }
                 }
             }
         }
-        __threadfence_block();
-        if (i + 2 < T) bf_bar_arrive(BF_BAR_FULL + b, BF_PIPE_THREADS);   // column sums of tile i consumed
     }
-    if (p.acq_mask) {
+    if (!p.acq_mask) return;
+    // the two finishing warps (warp 0 of each group) merge through shared memory
+    __shared__ BfBest red_best[3][2];
+    __shared__ BfTop2 red_top[2];
+    if (gw == 0) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) best[k] = bf_best_warp(best[k]);
 #pragma unroll
@@ -515,17 +466,27 @@ __global__ void __launch_bounds__(BF_PIPE_THREADS, 1) bf_posterior_pipe_kernel(P
             bf_top2_merge(top, t1v, i1, t2);
         }
         if (lane == 0) {
-            double* pv = p.part_val + ((size_t)set * p.tiles + blockIdx.x) * BF_NSLOT_VAL;
-            long long* pi = p.part_idx + ((size_t)set * p.tiles + blockIdx.x) * BF_NSLOT_IDX;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                pv[k] = best[k].v;
-                pi[k] = best[k].i;
-            }
-            pv[BF_SLOT_GREEDY] = top.t1;
-            pi[BF_SLOT_GREEDY] = top.i1;
-            pv[BF_SLOT_TOP2] = top.t2;
+            for (int k = 0; k < 3; ++k) red_best[k][grp] = best[k];
+            red_top[grp] = top;
         }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double* pv = p.part_val + ((size_t)set * p.tiles + blockIdx.x) * BF_NSLOT_VAL;
+        long long* pi = p.part_idx + ((size_t)set * p.tiles + blockIdx.x) * BF_NSLOT_IDX;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            BfBest a = red_best[k][0];
+            bf_best_take(a, red_best[k][1].v, red_best[k][1].i);
+            pv[k] = a.v;
+            pi[k] = a.i;
+        }
+        BfTop2 t = red_top[0];
+        bf_top2_merge(t, red_top[1].t1, red_top[1].i1, red_top[1].t2);
+        pv[BF_SLOT_GREEDY] = t.t1;
+        pi[BF_SLOT_GREEDY] = t.i1;
+        pv[BF_SLOT_TOP2] = t.t2;
     }
 }
 
@@ -591,18 +552,18 @@ extern "C" size_t bf_linv_packed_doubles(int n) {
     return bf_linv_block_off(nb);
 }
 
-// Tile / launch choice.  Pipelined kernel (two B tiles in shared memory, one 16-warp CTA per SM)
+// Tile / launch choice.  Dual-tile kernel (two B tiles in shared memory, one 16-warp CTA per SM)
 // whenever it fits; otherwise the single-buffer kernel with one CTA per SM.
-struct TileChoice { int NT; int pipe; };
-static size_t posterior_pipe_smem_bytes(int np, int NT, int d) {
-    return sizeof(double) * (2 * ((size_t)np * NT + (size_t)d * NT) + 5 * (size_t)BF_WARPS * NT + BF_MAX_DIM + BF_EXP_TAB_N);
+struct TileChoice { int NT; int dual; };
+static size_t posterior_dual_smem_bytes(int np, int NT, int d) {
+    return sizeof(double) * (2 * ((size_t)np * NT + (size_t)d * NT) + 4 * (size_t)BF_WARPS * NT + BF_MAX_DIM + BF_EXP_TAB_N);
 }
 static TileChoice choose_tile(int n) {
     const int np = bf_padded_n(n);
     const size_t cap = (size_t)227 * 1024 - 256;
-    const int pipe_nt[3] = {48, 24, 16};
+    const int dual_nt[3] = {48, 24, 16};
     for (int i = 0; i < 3; ++i)
-        if (posterior_pipe_smem_bytes(np, pipe_nt[i], BF_MAX_DIM) <= cap) return TileChoice{pipe_nt[i], 1};
+        if (posterior_dual_smem_bytes(np, dual_nt[i], BF_MAX_DIM) <= cap) return TileChoice{dual_nt[i], 1};
     const int one_nt[2] = {24, 16};
     for (int i = 0; i < 2; ++i)
         if (posterior_smem_bytes(np, one_nt[i], BF_MAX_DIM) <= cap) return TileChoice{one_nt[i], 0};
@@ -611,7 +572,7 @@ static TileChoice choose_tile(int n) {
 
 extern "C" int bf_posterior_tile(int n) { return choose_tile(n).NT; }
 
-// Partial-result slots (= CTAs) per set.  The pipelined kernel gives each CTA a chunk of
+// Partial-result slots (= CTAs) per set.  The dual-tile kernel gives each CTA a chunk of
 // consecutive tiles: about 8 CTAs per SM over the whole launch, at least 8 tiles per chunk.
 static void posterior_chunks(int n, long long N, int S, long long* ntiles, int* tpc, int* parts) {
     const TileChoice tc = choose_tile(n);
@@ -619,12 +580,13 @@ static void posterior_chunks(int n, long long N, int S, long long* ntiles, int* 
     if (tc.NT == 0 || N <= 0) return;
     const long long nt = (N + tc.NT - 1) / tc.NT;
     *ntiles = nt;
-    if (!tc.pipe) { *parts = (int)nt; return; }
+    if (!tc.dual) { *parts = (int)nt; return; }
     const long long sets = S > 0 ? S : 1;
     long long want = (148LL * 8 + sets - 1) / sets;    // CTAs per set
     if (want < 1) want = 1;
     long long per = (nt + want - 1) / want;
     if (per < 8) per = 8;
+    per += per & 1;            // whole tile pairs
     if (per > nt) per = nt;
     *tpc = (int)per;
     *parts = (int)((nt + per - 1) / per);
@@ -650,24 +612,24 @@ static int launch_posterior(const PostParams& p, dim3 grid, size_t smem, cudaStr
 }
 
 template <int D, int NTA>
-static int launch_posterior_pipe(const PostParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(bf_posterior_pipe_kernel<D, NTA>,
+static int launch_posterior_dual(const PostParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(bf_posterior_dual_kernel<D, NTA>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         bf_set_error("bf_gp_posterior: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
         return (int)e;
     }
-    bf_posterior_pipe_kernel<D, NTA><<<grid, BF_PIPE_THREADS, smem, st>>>(p);
+    bf_posterior_dual_kernel<D, NTA><<<grid, BF_DUAL_THREADS, smem, st>>>(p);
     BF_CHECK_LAUNCH("bf_gp_posterior");
     return 0;
 }
 
 template <int D>
-static int launch_posterior_tile(const PostParams& p, int pipe, dim3 grid, size_t smem, cudaStream_t st) {
-    if (pipe) {
-        if (p.NT == 48) return launch_posterior_pipe<D, 6>(p, grid, smem, st);
-        if (p.NT == 24) return launch_posterior_pipe<D, 3>(p, grid, smem, st);
-        return launch_posterior_pipe<D, 2>(p, grid, smem, st);
+static int launch_posterior_tile(const PostParams& p, int dual, dim3 grid, size_t smem, cudaStream_t st) {
+    if (dual) {
+        if (p.NT == 48) return launch_posterior_dual<D, 6>(p, grid, smem, st);
+        if (p.NT == 24) return launch_posterior_dual<D, 3>(p, grid, smem, st);
+        return launch_posterior_dual<D, 2>(p, grid, smem, st);
     }
     if (p.NT == 24) return launch_posterior<D, 3, 1>(p, grid, smem, st);
     return launch_posterior<D, 2, 1>(p, grid, smem, st);
@@ -701,19 +663,15 @@ extern "C" int bf_gp_posterior(int kern, long long N, int n, int d, int S, const
     p.curr_max = curr_max; p.xi = xi; p.kt = kt;
     p.part_val = part_val; p.part_idx = part_idx;
     posterior_chunks(n, N, S, &p.ntiles, &p.tpc, &p.tiles);
-    {
-        const char* dbg = getenv("BF_DEBUG_SKIP");
-        p.debug_skip = dbg ? atoi(dbg) : 0;
-    }
     BF_CHECK_ARG(S <= 65535, BF_ERR_SIZE, "bf_gp_posterior: at most 65535 sets per call (got %d)", S);
     dim3 grid(p.tiles, S);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = tc.pipe ? posterior_pipe_smem_bytes(p.np, p.NT, d) : posterior_smem_bytes(p.np, p.NT, d);
+    const size_t smem = tc.dual ? posterior_dual_smem_bytes(p.np, p.NT, d) : posterior_smem_bytes(p.np, p.NT, d);
     switch (d) {
-#define BF_CASE(DD) case DD: return launch_posterior_tile<DD>(p, tc.pipe, grid, smem, st);
+#define BF_CASE(DD) case DD: return launch_posterior_tile<DD>(p, tc.dual, grid, smem, st);
         BF_CASE(1) BF_CASE(2) BF_CASE(3) BF_CASE(4) BF_CASE(5) BF_CASE(6) BF_CASE(7) BF_CASE(8)
 #undef BF_CASE
-        default: return launch_posterior_tile<0>(p, tc.pipe, grid, smem, st);   // nDim 9..16 at run time
+        default: return launch_posterior_tile<0>(p, tc.dual, grid, smem, st);   // nDim 9..16 at run time
     }
     return BF_ERR_SIZE;
 }
