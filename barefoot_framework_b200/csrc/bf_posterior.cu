@@ -15,6 +15,8 @@
 //            and top-2 of the mean.
 // Two kernels: bf_posterior_dual_kernel (two tiles per CTA in lock step, used whenever two B tiles
 // fit in shared memory) and bf_posterior_kernel (one tile per CTA, larger n).
+#include <stdlib.h>
+
 #include "bf_common.cuh"
 
 struct PostParams {
@@ -31,6 +33,7 @@ struct PostParams {
     int tiles;            // partial slots per set (= CTAs per set)
     int tpc;              // tiles per CTA
     long long ntiles;     // candidate tiles per set
+    int debug_skip;       // profiling only (BF_DEBUG_SKIP): 1 = no phase B, 2 = no phase A, 4 = no phase C
 };
 
 // ---- phase A ------------------------------------------------------------------------------
@@ -418,11 +421,11 @@ __global__ void __launch_bounds__(BF_DUAL_THREADS, 1) bf_posterior_dual_kernel(P
             xs_s[e] = (active && gi < p.N) ? p.Xs[gi * dd + a] : 0.0;
         }
         __syncthreads();     // also orders the previous phase C before mpart / spart are rewritten
-        if (active) gen_tile<D, NTA>(p, w_s, xs_s, Bt, mpart, alpha, amp, tab_s, gw);
+        if (active && !(p.debug_skip & 2)) gen_tile<D, NTA>(p, w_s, xs_s, Bt, mpart, alpha, amp, tab_s, gw);
         __syncthreads();
-        if (active) dual_mma<NTA>(p.nb, Aset, Bt, spart, gw);
+        if (active && !(p.debug_skip & 1)) dual_mma<NTA>(p.nb, Aset, Bt, spart, gw);
         __syncthreads();
-        if (active && gw == 0) {
+        if (active && gw == 0 && !(p.debug_skip & 4)) {
             // ---- phase C: one lane per candidate (two rounds when the tile has 48) ----
 #pragma unroll
             for (int c = lane; c < NT; c += 32) {
@@ -663,6 +666,10 @@ extern "C" int bf_gp_posterior(int kern, long long N, int n, int d, int S, const
     p.curr_max = curr_max; p.xi = xi; p.kt = kt;
     p.part_val = part_val; p.part_idx = part_idx;
     posterior_chunks(n, N, S, &p.ntiles, &p.tpc, &p.tiles);
+    {
+        const char* dbg = getenv("BF_DEBUG_SKIP");   // profiling aid, results are wrong when set
+        p.debug_skip = dbg ? atoi(dbg) : 0;
+    }
     BF_CHECK_ARG(S <= 65535, BF_ERR_SIZE, "bf_gp_posterior: at most 65535 sets per call (got %d)", S);
     dim3 grid(p.tiles, S);
     cudaStream_t st = (cudaStream_t)stream;

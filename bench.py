@@ -289,7 +289,7 @@ def run_gpu(args):
         k_ms = float(np.mean(kern_ms))
         achieved = flop_per_launch / (k_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": achieved, "peak": dgemm, "unit": "TFLOP/s",
-                    "frac": achieved / dgemm, "traffic": None, "kernel": "bf_posterior_kernel<6,3,2>",
+                    "frac": achieved / dgemm, "traffic": None, "kernel": "bf_posterior_dual_kernel<6,3>",
                     "kernel_ms": k_ms, "kernel_share_of_step": k_ms * len(kern_ms) / ms,
                     "flop_per_launch": flop_per_launch,
                     "peak_source": "cuBLAS DGEMM 8192^3 (FP64 DMMA) measured in this run, best of 5; "
