@@ -1,0 +1,93 @@
+"""Multi-GPU plumbing for the hot path: one process per GPU (torchrun), no data-path collective.
+
+The reference shards work items evenly over SLURM nodes and collects one small record per item
+through pickle files (barefoot.py:2200-2209, subProcess.py:96-168).  Here the hyper-parameter sets
+(or, when there are fewer sets than ranks, the candidate tiles) are split across ranks and only
+the per-set (value, index) records are exchanged with torch.distributed (NCCL on GPUs; the same
+code runs on gloo/CPU tensors in the tests)."""
+import torch
+import torch.distributed as dist
+
+_BIG = 2 ** 62
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n, rank=None, world_size=None):
+    """Contiguous, balanced split of n units: returns (start, stop) of this rank
+    (the first n % world ranks get one extra unit)."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    base, extra = divmod(int(n), world_size)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def gather_sets(values, indices):
+    """Set-sharded stages: every rank holds (values [h_r], indices [h_r]) for its contiguous block of
+    hyper-parameter sets; returns the concatenation over ranks in set order on every rank."""
+    r, w = world()
+    if w == 1:
+        return values, indices
+    n_local = torch.tensor([values.numel()], dtype=torch.int64, device=values.device)
+    sizes = [torch.zeros_like(n_local) for _ in range(w)]
+    dist.all_gather(sizes, n_local)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(sizes)
+    pv = torch.zeros((m,), dtype=values.dtype, device=values.device)
+    pi = torch.zeros((m,), dtype=indices.dtype, device=indices.device)
+    pv[: values.numel()] = values
+    pi[: indices.numel()] = indices
+    gv = [torch.empty_like(pv) for _ in range(w)]
+    gi = [torch.empty_like(pi) for _ in range(w)]
+    dist.all_gather(gv, pv)
+    dist.all_gather(gi, pi)
+    return (torch.cat([g[:s] for g, s in zip(gv, sizes)]), torch.cat([g[:s] for g, s in zip(gi, sizes)]))
+
+
+def reduce_candidate_shards(values, indices, index_offset):
+    """Candidate-sharded stages (fewer sets than ranks): every rank holds the per-set maximum over
+    ITS candidates, (values [S], local indices [S]).  Returns the maximum over all candidates with
+    numpy's first-index tie rule (np.where(v == max)[0][0] over the concatenated candidate array,
+    acquisitionFunc.py:135-138): among equal values the lowest GLOBAL index wins."""
+    r, w = world()
+    gidx = indices + int(index_offset)
+    if w == 1:
+        return values, gidx
+    gv = [torch.empty_like(values) for _ in range(w)]
+    gi = [torch.empty_like(gidx) for _ in range(w)]
+    dist.all_gather(gv, values)
+    dist.all_gather(gi, gidx)
+    gv, gi = torch.stack(gv), torch.stack(gi)            # [world, S]
+    best = gv.max(dim=0).values
+    cand = torch.where(gv == best, gi, torch.full_like(gi, _BIG))
+    return best, cand.min(dim=0).values
+
+
+def reduce_top2(t1, i1, t2, index_offset):
+    """Candidate-sharded KG: combine per-rank (largest mean, its first global index, second largest)
+    into the global triple that bf_kg_diag needs."""
+    r, w = world()
+    gi1 = i1 + int(index_offset)
+    if w == 1:
+        return t1, gi1, t2
+    a = [torch.empty_like(t1) for _ in range(w)]
+    b = [torch.empty_like(gi1) for _ in range(w)]
+    c = [torch.empty_like(t2) for _ in range(w)]
+    dist.all_gather(a, t1)
+    dist.all_gather(b, gi1)
+    dist.all_gather(c, t2)
+    a, b, c = torch.stack(a), torch.stack(b), torch.stack(c)     # [world, S]
+    best = a.max(dim=0).values
+    is_best = a == best
+    first = torch.where(is_best, b, torch.full_like(b, _BIG)).min(dim=0).values
+    # second largest "by position": every first-place value except the winning one, and all seconds
+    winner = is_best & (b == first)
+    others = torch.where(winner, torch.full_like(a, float("-inf")), a)
+    second = torch.maximum(others.max(dim=0).values, c.max(dim=0).values)
+    return best, first, second

@@ -185,25 +185,11 @@ def measure_dgemm_tflops(torch, n=8192, reps=5):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def reduce_records(torch, dist, vals, idxs, rank, world, n_per_rank):
-    """All-gather the per-rank (value, global index) rows and keep the first maximum (np.where(v == max)[0][0]
-    over the concatenated candidate array, acquisitionFunc.py:135-138)."""
-    if world == 1:
-        return vals, idxs
-    gv = [torch.empty_like(vals) for _ in range(world)]
-    gi = [torch.empty_like(idxs) for _ in range(world)]
-    dist.all_gather(gv, vals)
-    dist.all_gather(gi, idxs + rank * n_per_rank)
-    gv, gi = torch.stack(gv), torch.stack(gi)           # [world, 3]
-    best = gv.max(dim=0).values
-    cand = torch.where(gv == best, gi, torch.full_like(gi, 2 ** 62))
-    return best, cand.min(dim=0).values
-
-
 def run_gpu(args):
     import torch
     import torch.distributed as dist
     from barefoot_framework_b200 import _lib, engine
+    from barefoot_framework_b200 import dist as bdist
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -228,7 +214,9 @@ def run_gpu(args):
         f = engine.build_factors(KERNEL, Xt, yt, hp[:, 1:], hp[:, 0], sn, ndim=N_DIM, check=False)
         res = engine.posterior_sweep(f, Xs_dev, acq_mask=mask, spread_is_sqrt=False, curr_max=curr_max,
                                      xi=XI, kt=kt)
-        return reduce_records(torch, dist, res.best_val[0, :3], res.best_idx[0, :3], rank, world, N_CAND)
+        # candidate-sharded: per-rank maxima -> all-gather -> first global index among equal values
+        return bdist.reduce_candidate_shards(res.best_val[0, :3].contiguous(), res.best_idx[0, :3].contiguous(),
+                                             rank * N_CAND)
 
     def step_e2e(b):
         Xs_dev = host_batches[b].to(dev, non_blocking=True)
