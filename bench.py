@@ -285,21 +285,22 @@ def run_gpu(args):
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tr):      # dram__bytes_read+write per launch from the committed ncu --set full capture
             for k, v in json.load(open(tr)).items():
-                if k.startswith("bf_posterior_kernel"):
+                if k.startswith("bf_posterior"):
                     roofline["traffic"] = v["dram_bytes_per_launch"]
                     roofline["traffic_source"] = v["source"]
         peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.isfile(peaks):
             roofline["hbm_gbs_measured"] = json.load(open(peaks)).get("hbm_gbs")
         cpu_steps = 2
-        cpu_val, _ = cpu_throughput(cpu_steps, 1)
+        cpu_val = cpu_throughput(cpu_steps, 1)[0] if world == 1 else None      # N = 1 only (contract)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
                 "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(world),
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / steps},
-                "roofline": roofline, "cpu_baseline": cpu_baseline_dict(cpu_val, CPU_SAMPLE, cpu_steps),
+                "roofline": roofline,
+                "cpu_baseline": cpu_baseline_dict(cpu_val, CPU_SAMPLE, cpu_steps) if world == 1 else None,
                 "selected": {"EI": int(out[1][0]), "PI": int(out[1][1]), "UCB": int(out[1][2])}}
         print(json.dumps(line))
     if world > 1:
