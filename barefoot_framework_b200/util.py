@@ -337,3 +337,134 @@ def evaluateFusedModel(param):
     (finish, reification, x_fused, fused_model_HP, kernel, x_test, curr_max, xi, acqIndex) = data[param[0]]
     mu = evaluate_fused_model_batch(model_temp, reification, x_fused, np.asarray(fused_model_HP)[None], kernel, x_test)
     return [acqIndex, mu[0]]
+
+
+# ---------------------------------------------------------------------------------------------
+# design-space sampling and constraints (host side, O(N d); util.py:57-214 of the reference)
+# ---------------------------------------------------------------------------------------------
+def lhs(n, samples=None):
+    """pyDOE.lhs(n, samples) with criterion None ("classic"), on the GLOBAL legacy numpy RNG like
+    pyDOE: one uniform draw per stratum and column (a single rand(samples, n) call), then an
+    independent np.random.permutation per column.  pyDOE is an unpinned third-party dependency of
+    the reference (util.py:9); this follows its published algorithm so seeded runs reproduce."""
+    samples = n if samples is None else samples
+    edges = np.linspace(0, 1, samples + 1)
+    u = np.random.rand(samples, n)
+    lo, hi = edges[:samples], edges[1:samples + 1]
+    pts = u * (hi - lo)[:, None] + lo[:, None]
+    out = np.empty_like(pts)
+    for j in range(n):
+        out[:, j] = pts[np.random.permutation(range(samples)), j]
+    return out
+
+
+def cartesian(*arrays):
+    """util.py:57-65: all combinations of the per-dimension arrays, one column per dimension."""
+    mesh = np.meshgrid(*arrays)
+    return np.reshape(np.concatenate(mesh).ravel(), (len(mesh), mesh[0].size)).T
+
+
+def composition_sampler(ndim, nsamples):
+    """util.py:67-70."""
+    X = -np.log(lhs(ndim + 1, nsamples))
+    X = X / np.sum(X, axis=1)[:, None]
+    return X[:, 0:ndim]
+
+
+def sampleDesignSpace(ndim, nsamples, sampleScheme):
+    """util.py:72-102: "LHS", "Grid" (smallest full factorial grid with at least nsamples points),
+    "Custom" (rows of data/possibleInputs.csv topped up with LHS) or "CompFunc"."""
+    import pandas as pd
+    if sampleScheme == "LHS":
+        x = lhs(ndim, nsamples)
+    if sampleScheme == "Grid":
+        for per_axis in range(1, nsamples):
+            x = cartesian(*([np.linspace(0, 1, per_axis)] * ndim))
+            if x.shape[0] >= nsamples:
+                return x
+    if sampleScheme == "Custom":
+        dfInputs = pd.read_csv("data/possibleInputs.csv", index_col=0)
+        if dfInputs.shape[0] > nsamples:
+            x = dfInputs.sample(n=nsamples)
+        else:
+            extra = pd.DataFrame(lhs(ndim, nsamples - dfInputs.shape[0]), columns=dfInputs.columns)
+            x = pd.concat((dfInputs, extra))
+    if sampleScheme == "CompFunc":
+        x = composition_sampler(ndim, nsamples)
+    return np.array(x)
+
+
+def _given(v):
+    return not (isinstance(v, list) and len(v) == 0)
+
+
+def apply_constraints(samples, ndim, resolution=[], A=[], b=[], Aeq=[], beq=[],
+                      lb=[], ub=[], func=[], sampleScheme="LHS", opt_sample_size=True,
+                      evaluatedPoints=[]):
+    """util.py:104-214: sample the design space and keep the rows whose violation count is zero.
+
+    Semantics kept from the reference, including its conventions: a row is rejected when
+    ``A * x <= b`` / ``Aeq * x <= beq`` holds in any column, when any coordinate is below lb or
+    above ub, when a constraint function returns non-zero, or when the point has already been
+    evaluated by EVERY model in evaluatedPoints.  With opt_sample_size the sample is grown by
+    100 * samples per retry until enough rows survive (up to 2000 * ndim times the request)."""
+    pending = np.zeros(5)
+    pending[0] = 1 if _given(A) else 0
+    pending[1] = 1 if _given(Aeq) else 0
+    pending[2] = 1 if _given(lb) else 0
+    pending[3] = 1 if _given(ub) else 0
+    if _given(func):
+        pending[4] = len(func) if isinstance(func, list) else 1
+    draw = samples
+    best_rows, best_count = [], 0
+    while True:
+        try:
+            x = sampleDesignSpace(ndim, draw, sampleScheme)
+        except Exception:
+            x = sampleDesignSpace(ndim, draw, "LHS")
+        if _given(resolution):
+            x = np.round(x, decimals=resolution)
+        hits = np.zeros((x.shape[0], ndim))
+        if _given(A) and _given(b) and len(A) == ndim:
+            hits += np.tile(np.array(A), (x.shape[0], 1)) * x <= b
+            pending[0] = 0
+        if _given(Aeq) and _given(beq):
+            hits += np.tile(np.array(Aeq), (x.shape[0], 1)) * x <= beq
+            pending[1] = 0
+        if _given(lb) and len(lb) == ndim:
+            hits += x < np.array(lb).reshape((1, ndim))
+            pending[2] = 0
+        if _given(ub) and len(ub) == ndim:
+            hits += x > np.array(ub).reshape((1, ndim))
+            pending[3] = 0
+        violations = np.sum(hits, axis=1)
+        if isinstance(func, list) and _given(func):
+            for fn in func:
+                try:
+                    violations += fn(x)
+                    pending[4] -= 1
+                except Exception:
+                    pass
+        elif not isinstance(func, list):
+            try:
+                violations += func(x)
+                pending[4] = 0
+            except Exception:
+                pass
+        if _given(evaluatedPoints):
+            seen = np.zeros_like(violations)
+            for pts in evaluatedPoints:
+                seen += (x[:, None] == pts).all(-1).any(-1)
+            seen[np.where(seen < len(evaluatedPoints))] = 0
+            violations += seen
+        keep = np.where(violations == 0)[0]
+        if not opt_sample_size:
+            return x[keep, :], True
+        if keep.shape[0] >= samples:
+            return x[keep[0:samples], :], bool(np.sum(pending) == 0)
+        if len(keep) > best_count:
+            best_count, best_rows = len(keep), x[keep, :]
+        if draw / samples < ndim * 2000:
+            draw += samples * 100
+        else:
+            return best_rows, False

@@ -1,0 +1,91 @@
+"""The toy information sources of BASELINE config #1 (the reduced-order models and the truth
+function of the reference's sample_code.py:15-37), written as small Fourier-style sums on the
+unit square.  Shared by oracle/gen_config1.py (verbatim reference run) and the GPU tests."""
+import numpy as np
+
+
+def _angles(x):
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x[None, :]
+    return np.pi * (x * 2 - 1)
+
+
+def _series(x, terms):
+    """Left-to-right sum of num * sin(freq * angle[axis]) / (den * pi) terms; den None means the
+    pi * sin(.) / 2 term.  Order and association follow sample_code.py so values are bit-identical."""
+    t = _angles(x)
+    total = None
+    for num, freq, axis, den in terms:
+        if den is None:
+            term = np.pi * np.sin(freq * t[:, axis]) / 2
+        else:
+            term = num * np.sin(freq * t[:, axis]) / (den * np.pi)
+        total = term if total is None else total + term
+    return total
+
+
+def rom1(x):
+    return _series(x, [(-80, 2, 0, 441), (-160, 4, 0, 81), (1, 5, 0, None), (-48, 1, 1, 1225), (-16, 3, 1, 81),
+                       (-240, 5, 1, 121)])
+
+
+def rom2(x):
+    return _series(x, [(-60, 2.5, 0, 441), (-60, 0.5, 1, 1200), (-160, 4.2, 0, 81), (1, 5.3, 0, None),
+                       (-16, 3.2, 1, 81), (-240, 5.3, 1, 121)])
+
+
+def rom3(x):
+    return _series(x, [(-100, 1.5, 0, 400), (-36, 1.5, 1, 1200), (-160, 4.5, 0, 81), (1, 5.5, 0, None),
+                       (-16, 3.5, 1, 81), (-240, 5.5, 1, 121)])
+
+
+def truth(x):
+    t = _angles(x)
+    return np.abs(t[:, 0]) * np.sin(5 * t[:, 0]) + np.abs(t[:, 1]) * np.sin(6 * t[:, 1])
+
+
+MODEL_PARAM = {'model_l': [[0.1608754, 0.2725361], [0.17094462, 0.28988983], [0.10782092, 0.18832378]],
+               'model_sf': [6.95469898, 8.42299498, 2.98009081],
+               'model_sn': [0.05, 0.05, 0.05],
+               'means': [-2.753353101070388e-16, -1.554312234475219e-16, 4.884981308350689e-17],
+               'std': [1.2460652976290285, 1.3396622409903254, 1.3429644403939915],
+               'err_l': [[0.1, 0.1], [0.1, 0.1], [0.1, 0.1]],
+               'err_sf': [1, 1, 1],
+               'err_sn': [0.01, 0.01, 0.01],
+               'costs': [1, 1, 1, 1]}
+
+# (name, constructor keywords, initialize_parameters keywords, seed)
+CASES = [
+    ("config1_se_kg", dict(reification=True, acquisitionFunc="KG", tmSampleOpt="KG", initDataPathorNum=[2, 2, 2, 2]),
+     dict(covFunc="SE", iterLimit=2, sampleCount=10, hpCount=20, batchSize=2, tmIter=1, fusedPoints=10,
+          fusedSamples=200), 0),
+    ("reifi_m52_ei", dict(reification=True, acquisitionFunc="EI", tmSampleOpt="EI", initDataPathorNum=[3, 3, 3, 3]),
+     dict(covFunc="M52", iterLimit=2, sampleCount=8, hpCount=12, batchSize=3, tmIter=1, fusedPoints=12,
+          fusedSamples=100), 1),
+    ("reifi_m32_ucb_greedy", dict(reification=True, acquisitionFunc="UCB", tmSampleOpt="Greedy",
+                                   initDataPathorNum=[3, 2, 3, 2]),
+     dict(covFunc="M32", iterLimit=2, sampleCount=8, hpCount=10, batchSize=2, tmIter=1, fusedPoints=10,
+          fusedSamples=80), 2),
+    ("batch_only_ei", dict(reification=False, acquisitionFunc="EI", tmSampleOpt="EI", initDataPathorNum=[4]),
+     dict(covFunc="M32", iterLimit=3, sampleCount=30, hpCount=25, batchSize=3, tmIter=5, fusedPoints=10,
+          fusedHP=[3, 0.1, 0.1]), 3),
+]
+
+
+def run_case(barefoot_cls, name, ctor, init, seed, workdir):
+    """Run one case in `workdir` with the given barefoot class; returns (evaluatedPoints, iterationData)."""
+    import os
+    cwd = os.getcwd()
+    os.chdir(workdir)
+    try:
+        np.random.seed(seed)
+        roms = [rom1, rom2, rom3] if ctor["reification"] else []
+        fw = barefoot_cls(ROMModelList=roms, TruthModel=truth, calcInitData=True, multiNode=0, workingDir=".",
+                          calculationName=name, nDim=2, input_resolution=5, sampleScheme="LHS", logname="BAREFOOT_" + name,
+                          maximize=True, batch=True, **ctor)
+        assert fw.initialize_parameters(modelParam=MODEL_PARAM, **init) is not False
+        assert fw.run_optimization() is not False
+        return np.array(fw.evaluatedPoints, dtype=np.float64), np.array(fw.iterationData, dtype=np.float64)
+    finally:
+        os.chdir(cwd)
