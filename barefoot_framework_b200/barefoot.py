@@ -228,10 +228,10 @@ class barefoot():
                 m = job["Model Index"]
                 if m != -1:
                     self.ROMInitInput[m][filled[m], :] = job["Input Values"]
-                    self.ROMInitOutput[m][filled[m]] = self.goal * results
+                    self.ROMInitOutput[m][filled[m]] = np.asarray(self.goal * results).reshape(-1)[0]
                 else:
                     self.TMInitInput[filled[m], :] = job["Input Values"]
-                    self.TMInitOutput[filled[m]] = self.goal * results
+                    self.TMInitOutput[filled[m]] = np.asarray(self.goal * results).reshape(-1)[0]
                     if np.max(results) > self.maxTM:
                         self.maxTM = np.max(results)
                 filled[m] += 1
