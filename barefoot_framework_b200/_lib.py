@@ -39,6 +39,8 @@ SIGNATURES = {
     "bf_kg_tiles": (c_i, [c_ll]),
     "bf_top2": (c_i, [c_ll, c_i, c_p, c_p, c_p, c_p]),
     "bf_kg_diag": (c_i, [c_ll, c_ll, c_i, c_p, c_p, c_p, c_p, c_d, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "bf_kg_full_max_n": (c_i, []),
+    "bf_kg_full": (c_i, [c_i, c_ll, c_i, c_p, c_p, c_d, c_p, c_p, c_p, c_p]),
     "bf_acq_tiles": (c_i, [c_ll]),
     "bf_acq_eval": (c_i, [c_i, c_ll, c_i, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_p]),
     "bf_reification": (c_i, [c_i, c_ll, c_p, c_p, c_p, c_p, c_p]),
@@ -95,7 +97,7 @@ def stream():
 
 
 # kernels per exported call, for the launch counter
-_KERNELS_PER_CALL = {"bf_kg_diag": 2, "bf_acq_eval": 2, "bf_gp_solve_rows": 3}
+_KERNELS_PER_CALL = {"bf_kg_diag": 2, "bf_acq_eval": 2, "bf_gp_solve_rows": 3, "bf_kg_full": 2}
 
 
 def call(name, *args):

@@ -29,7 +29,7 @@ def knowledge_gradient(M, sn, mu, sigma):
         diag = np.diag(sigma)
         if np.count_nonzero(sigma) != np.count_nonzero(diag):
             nu_star, x_star, nu = engine.kg_full(mu, sigma, M=int(M), sn=float(sn))
-            return _kg_result(nu_star, x_star, nu)
+            return _kg_result(nu_star, x_star, nu[0])
         sigma = diag
     if mu.shape[0] < 2:
         # a single candidate: one line only, sig = 0 -> log(0) = -inf -> floor (0, 0)

@@ -214,11 +214,36 @@ def posterior_cov(f, Xa, Xb=None, set_index=0):
 
 
 def kg_full(mu, sigma, M=None, sn=SN_KG):
-    raise NotImplementedError("knowledge gradient on a dense covariance (SURVEY.md 8f rank 3) is not built yet")
+    """knowledge_gradient(M, sn, mu, sigma) with a dense covariance (acquisitionFunc.py:12-96):
+    mu [N] or [S, N], sigma [N, N] or [S, N, N].  Returns device tensors (kg_val [S], kg_idx [S], nu [S, M])."""
+    mu = to_dev(mu)
+    mu2 = mu.reshape(1, -1) if mu.dim() == 1 else mu
+    S, N = mu2.shape
+    sg = to_dev(sigma).reshape(S, N, N)
+    M = N if M is None else int(M)
+    nu = torch.empty((S, max(M, 1)), dtype=F64, device=mu2.device)
+    kg_val = torch.empty((S,), dtype=F64, device=mu2.device)
+    kg_idx = torch.empty((S,), dtype=torch.int64, device=mu2.device)
+    st = stream()
+    for s0 in range(0, S, 65535):
+        sc = min(65535, S - s0)
+        call("bf_kg_full", N, M, sc, mu2[s0:].data_ptr(), sg[s0:].data_ptr(), float(sn), nu[s0:].data_ptr(),
+             kg_val[s0:].data_ptr(), kg_idx[s0:].data_ptr(), st)
+    return kg_val, kg_idx, nu[:, :M]
 
 
 def kg_full_from_factors(f, x_test, shift=0.0, sn=SN_KG):
-    raise NotImplementedError("knowledge gradient on a dense covariance (SURVEY.md 8f rank 3) is not built yet")
+    """Batch-only KG (util.py:952,1078-1081): per set, the full posterior covariance at x_test
+    (predict_cov) followed by the dense knowledge gradient.  Returns host arrays (values [S], indices [S])."""
+    xs = to_dev(x_test).reshape(len(x_test), -1)
+    vals, idxs = np.empty(f.S), np.empty(f.S, dtype=np.int64)
+    for s in range(f.S):
+        mean, cov = posterior_cov(f, xs, set_index=s)
+        if shift:
+            mean = mean + float(shift)
+        v, i, _ = kg_full(mean, cov, sn=sn)
+        vals[s], idxs[s] = float(v[0].item()), int(i[0].item())
+    return vals, idxs
 
 
 def kg_from_sweep(res, M=None, sn=SN_KG, want_nu=False):

@@ -151,6 +151,16 @@ int bf_acq_eval(int kind, long long N, int S, const double* y, const double* spr
                 double curr_max, double xi, double kt, double* out, double* part_val,
                 long long* part_idx, double* best_val, long long* best_idx, void* stream);
 
+/* ---- (4) knowledge gradient on a DENSE covariance (Frazier's sort / unique / upper-envelope
+ * algorithm): acquisitionFunc.py:12-96 as the batch-only path calls it, util.py:1078-1081 ------- */
+/* mu [S x N], sigma [S x N x N] (column i of sigma is read for candidate i, as the reference does),
+ * candidates i < M scored.  nu_out [S x M] receives every log-KG value; kg_val / kg_idx [S] the
+ * running maximum from the reference's floor (0, 0).  N <= BF_KG_FULL_MAX_N. */
+#define BF_KG_FULL_MAX_N 4096
+int bf_kg_full_max_n(void);
+int bf_kg_full(int N, long long M, int S, const double* mu, const double* sigma, double sn,
+               double* nu_out, double* kg_val, long long* kg_idx, void* stream);
+
 /* ---- (3) reification: reificationFusion.py:26-57 ------------------------------------------- */
 /* y, var: [m x P] (model-major).  mean_f, var_f: [P].  pinv semantics of numpy (rcond 1e-15). */
 int bf_reification(int m, long long P, const double* y, const double* var,

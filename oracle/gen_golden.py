@@ -85,6 +85,46 @@ def gen_kg(ref):
     np.savez_compressed(os.path.join(OUT, "kg.npz"), **out)
 
 
+def gen_kg_full(ref):
+    """knowledge_gradient on DENSE covariances (the batch-only path, util.py:1078-1081)."""
+    rng = np.random.default_rng(808)
+    kg = ref["acquisitionFunc"].knowledge_gradient
+    out = {}
+    cases = []
+    for n in (2, 5, 33, 120):
+        B = rng.normal(size=(n, max(2, n // 3)))
+        sigma = B @ B.T / B.shape[1] + 1e-3 * np.eye(n)        # smooth-ish SPD, correlated columns
+        cases.append((rng.normal(size=n), sigma, n))
+    # posterior-like covariance with duplicated candidates (equal slopes -> the unique/max step) and M < N
+    n = 40
+    x = np.sort(rng.uniform(size=n))
+    x[7] = x[3]
+    x[21] = x[20]
+    K = np.exp(-0.5 * (x[:, None] - x[None, :]) ** 2 / 0.05)
+    xt = rng.uniform(size=6)
+    Ks = np.exp(-0.5 * (x[:, None] - xt[None, :]) ** 2 / 0.05)
+    Kt = np.exp(-0.5 * (xt[:, None] - xt[None, :]) ** 2 / 0.05) + 0.01 * np.eye(6)
+    sigma = K - Ks @ np.linalg.solve(Kt, Ks.T)
+    sigma = 0.5 * (sigma + sigma.T)
+    mu = np.sin(6 * x)
+    mu[7] = mu[3] + 0.1
+    cases.append((mu, sigma, n))
+    cases.append((mu.copy(), sigma.copy(), 25))
+    # large variances: log-KG values above the floor, so the arg-max is exercised
+    for n in (12, 64):
+        B = rng.normal(size=(n, n))
+        cases.append((0.1 * rng.normal(size=n), 40.0 * (B @ B.T / n + 0.05 * np.eye(n)), n))
+    for k, (mu, sigma, M) in enumerate(cases):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            nu_star, x_star, NU = kg(M, 0.1, mu, sigma)
+        out[f"mu_{k}"], out[f"sigma_{k}"], out[f"M_{k}"] = mu, sigma, np.int64(M)
+        out[f"nu_star_{k}"], out[f"x_star_{k}"] = np.float64(nu_star), np.int64(x_star)
+        out[f"NU_{k}"] = np.array(NU, dtype=np.float64)
+    out["ncases"] = np.int64(len(cases))
+    np.savez_compressed(os.path.join(OUT, "kg_full.npz"), **out)
+
+
 def gen_acq(ref):
     rng = np.random.default_rng(303)
     af = ref["acquisitionFunc"]
@@ -323,6 +363,7 @@ def main():
     ref = ref_loader.load_reference()
     gen_reification(ref)
     gen_kg(ref)
+    gen_kg_full(ref)
     gen_acq(ref)
     gen_gp(ref)
     gen_workitems(ref)

@@ -206,3 +206,32 @@ def test_batch_only_path(pkg):
                                                           iteration=2)
             np.testing.assert_array_equal(idxs, g[pre + f"{opt}_idx"], err_msg=kern + opt)
             np.testing.assert_allclose(vals, g[pre + f"{opt}_val"], rtol=1e-8, atol=1e-11, err_msg=kern + opt)
+
+
+def test_knowledge_gradient_dense_covariance(pkg):
+    """bf_kg_full against knowledge_gradient(M, 0.1, mu, sigma) of the verbatim reference on dense
+    covariances (sort / unique-with-max / upper envelope), including duplicated slopes and M < N."""
+    af = pkg.acquisitionFunc
+    g = golden("kg_full.npz")
+    for k in range(int(g["ncases"])):
+        mu, sigma, M = g[f"mu_{k}"], g[f"sigma_{k}"], int(g[f"M_{k}"])
+        nu_star, x_star, NU = af.knowledge_gradient(M, 0.1, mu, sigma)
+        assert x_star == int(g[f"x_star_{k}"]), k
+        ref = float(g[f"nu_star_{k}"])
+        assert abs(nu_star - ref) <= REL * max(1.0, abs(ref)), k
+        NU, ref_nu = np.asarray(NU), g[f"NU_{k}"]
+        fin = np.isfinite(ref_nu)
+        assert np.array_equal(np.isfinite(NU), fin), k
+        assert np.abs(NU[fin] - ref_nu[fin]).max(initial=0) <= REL * np.abs(ref_nu[fin]).max(initial=1.0), k
+
+
+def test_batch_only_path_kg_uses_full_covariance(pkg):
+    g = golden("batch.npz")
+    d = int(g["d"])
+    for kidx in range(3):
+        pre = f"k{kidx}_"
+        kern = str(g[pre + "kern"])
+        gp = pkg.gpModel.gp_model(g["x"], g["y"], np.ones(d), 1, 0.05, d, kern)
+        vals, idxs = pkg.util.batch_acquisition_batch(gp, g["hps"], g["x_test"], float(g["curr_max"]), "KG", iteration=2)
+        np.testing.assert_array_equal(idxs, g[pre + "KG_idx"], err_msg=kern)
+        np.testing.assert_allclose(vals, g[pre + "KG_val"], rtol=1e-7, atol=1e-10, err_msg=kern)

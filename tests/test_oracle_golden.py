@@ -34,6 +34,19 @@ def test_kg_closed_form_equals_reference_loop():
         np.testing.assert_array_equal(nu[fin], ref[fin])
 
 
+def test_kg_dense_covariance_equals_reference():
+    g = golden("kg_full.npz")
+    for k in range(int(g["ncases"])):
+        mu, sigma, M = g[f"mu_{k}"], g[f"sigma_{k}"], int(g[f"M_{k}"])
+        nu_star, x_star, nu = fast.kg_full(mu, sigma, 0.1, M)
+        assert x_star == int(g[f"x_star_{k}"]), k
+        np.testing.assert_allclose(nu_star, float(g[f"nu_star_{k}"]), rtol=1e-12, atol=0)
+        ref = g[f"NU_{k}"]
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(nu), fin), k
+        np.testing.assert_allclose(nu[fin], ref[fin], rtol=1e-11, atol=1e-13)
+
+
 def test_elementwise_acquisitions():
     g = golden("acq.npz")
     y, std = g["y"], g["std"]

@@ -1,0 +1,155 @@
+#!/usr/bin/env python
+"""Measurements for BASELINE configs #3, #4 and #5 - not the bench.py headline line.
+
+    python tools/bench_configs.py --config 3 [--H 1000] [--N 100000]      (torchrun for > 1 GPU)
+    python tools/bench_configs.py --config 4 [--N 100000]
+    python tools/bench_configs.py --config 5 [--H 1000] [--N 1000000]
+
+Prints one JSON line per config with the stage timings (CUDA events, max over ranks)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def lhs(rng, n, d):
+    u = rng.uniform(size=(n, d))
+    cut = np.linspace(0, 1, n + 1)
+    pts = cut[:n, None] + u * (cut[1:, None] - cut[:n, None])
+    for j in range(d):
+        pts[:, j] = pts[rng.permutation(n), j]
+    return pts
+
+
+def toy(x, shift):
+    return np.sum(np.sin(2 * np.pi * (x + shift)), axis=1) + 0.3 * np.sum(x, axis=1)
+
+
+def hp_grid(rng, H, d, low=1e-4, up=1.0):
+    top = low * 10
+    grid = np.linspace(low, top, num=H)
+    while top < up:
+        bottom, top = top, min(top * 10, up)
+        grid = np.append(grid, np.linspace(bottom, top, num=H))
+    return grid[rng.integers(0, grid.shape[0], size=(H, d + 1))]
+
+
+def timed(torch, fn, reps=1):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+
+
+def config_reification_kg(args, N, H, tag):
+    import torch
+    import torch.distributed as dist
+    from barefoot_framework_b200 import dist as bdist, engine
+    from barefoot_framework_b200.reificationFusion import model_reification
+    rank, world = bdist.world()
+    d, m, F = 6, 3, 500
+    rng = np.random.default_rng(0)
+    x_train = [np.round(lhs(rng, 200, d), 5) for _ in range(m)]
+    y_train = [toy(x, s) for x, s in zip(x_train, (0.05, 0.12, -0.07))]
+    x_true = np.round(lhs(rng, 50, d), 5)
+    y_true = toy(x_true, 0.0) + 0.2 * np.sum(x_true ** 2, axis=1)
+    hp_rom = rng.uniform(0.1, 0.5, size=(m, d))
+    model = model_reification(x_train, y_train, hp_rom, [1.0] * m, [0.05] * m, [float(np.mean(y)) for y in y_train],
+                              [float(np.std(y)) for y in y_train], rng.uniform(0.1, 0.5, size=(m, d)), [1.0] * m,
+                              [0.01] * m, x_true, y_true, m, d, "M52")
+    x_fused = np.round(lhs(rng, F, d), 5)
+    x_test = engine.to_dev(np.round(lhs(rng, N, d), 5))
+    hps = hp_grid(rng, H, d)
+    a, b = bdist.shard_range(H)
+    my_hp = hps[a:b]
+    t_targets, targets = timed(torch, lambda: model.fused_targets_device(x_fused))
+    t_setup, (f, scale, shift) = timed(torch, lambda: model.create_fused_GP_batch(x_fused, my_hp, "M52", targets=targets))
+    # sets with an ill-conditioned kernel matrix raise in the reference; here they are reported
+    events = []
+    engine.posterior_events = events
+    t_sweep, res = timed(torch, lambda: engine.posterior_sweep(f, x_test, scale, shift, want_mu=True, want_var=True,
+                                                               acq_mask=engine.ACQ_GREEDY, curr_max=float(y_true.max())))
+    engine.posterior_events = None
+    t_post = sum(x.elapsed_time(y) for x, y in events)
+    t_kg, (kv, ki, _) = timed(torch, lambda: engine.kg_from_sweep(res))
+    t_gather, (gv, gi) = timed(torch, lambda: bdist.gather_sets(kv, ki))
+    # reification kernel on a large stand-alone batch (HBM roofline)
+    P = 10 ** 7
+    ym = torch.randn((m, P), dtype=torch.float64, device="cuda")
+    sv = torch.rand((m, P), dtype=torch.float64, device="cuda") + 0.05
+    t_reif, _ = timed(torch, lambda: engine.reification(ym, sv), reps=5)
+    total = t_targets + t_setup + t_sweep + t_kg + t_gather
+    if world > 1:
+        t = torch.tensor([total, t_post, t_kg, t_setup], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total, t_post, t_kg, t_setup = [float(v) for v in t]
+    if rank == 0:
+        h_local = b - a
+        flop_eval = F * F + F * (3 * d + 8)
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(
+            os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+        line = {"config": tag, "n_gpus": world, "N": N, "H": H, "F": F, "m": m, "d": d, "kernel": "M52",
+                "evals_per_s_end_to_end": N * H / (total * 1e-3),
+                "ms": {"fused_targets": t_targets, "setup_sets": t_setup, "posterior_kernel": t_post,
+                       "posterior_sweep_incl_finalize": t_sweep, "kg": t_kg, "gather": t_gather, "total": total},
+                "posterior_tflops": N * h_local * flop_eval / (t_post * 1e-3) / 1e12,
+                "kg_gbs": N * h_local * 16 / (t_kg * 1e-3) / 1e9, "kg_frac_of_hbm": N * h_local * 16 / (t_kg * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "reification_gbs": P * (16 * m + 16) / (t_reif * 1e-3) / 1e9,
+                "reification_frac_of_hbm": P * (16 * m + 16) / (t_reif * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "selected_first8": [int(v) for v in gi[:8].cpu()]}
+        print(json.dumps(line))
+
+
+def config_kmedoids(args, N):
+    import torch
+    from barefoot_framework_b200 import engine
+    rng = np.random.default_rng(0)
+    k = 10
+    X = np.column_stack([np.exp(rng.normal(size=N)), rng.integers(0, 10 ** 6, size=N).astype(float),
+                         rng.integers(0, 3, size=N).astype(float)])
+    Xd = engine.to_dev(X)
+    t_rowsum, rs = timed(torch, lambda: engine.kmedoids_rowsum(Xd))
+    t0 = time.perf_counter()
+    med, labels, n_iter = engine.kmedoids_fit(Xd, k, rowsum=rs)
+    torch.cuda.synchronize()
+    t_fit = (time.perf_counter() - t0) * 1e3
+    print(json.dumps({"config": "#4 k-medoids", "N": N, "f": 3, "k": k, "ms": {"rowsum": t_rowsum, "alternate_loop": t_fit},
+                      "iterations": n_iter, "rowsum_pairs_per_s": N * N / (t_rowsum * 1e-3),
+                      "medoids": [int(v) for v in med]}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, required=True)
+    ap.add_argument("--N", type=int, default=0)
+    ap.add_argument("--H", type=int, default=1000)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.config == 3:
+        config_reification_kg(args, args.N or 10 ** 5, args.H, "#3 reification + KG, M52")
+    elif args.config == 5:
+        config_reification_kg(args, args.N or 10 ** 6, args.H, "#5 full iteration (TM-stage grid), M52 + KG")
+    elif args.config == 4:
+        config_kmedoids(args, args.N or 10 ** 5)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
