@@ -89,6 +89,268 @@ __device__ __forceinline__ void bf_tile_abt(double (&c)[4][4][2], const double* 
     }
 }
 
+// ---- panel-in-shared-memory variants (n <= BF_SETUP_RL_MAX_NP): 8 warps, one CTA per matrix ------
+// The left-looking kernels below read both DMMA operands from L2 inside every k-step, which makes a
+// single 500 x 500 factorisation latency-bound (1.7 ms + 0.5 ms).  Here the operand every tile of a
+// step shares is staged in shared memory once per step:
+//   Cholesky (right-looking): the freshly solved panel column P = A[k+1:, k] L_kk^-T; the trailing
+//   update A[i, j] -= P_i P_j^T then runs with both operands in shared memory, up to 120 tiles
+//   spread over the warps;
+//   inverse (row by row): W = L_II^-1 L[I, 0:I], after which L^-1[I, J] = - sum_K W_IK L^-1[K, J].
+#define BF_RL_WARPS 8
+#define BF_RL_THREADS (BF_RL_WARPS * 32)
+#define BF_RL_PLD 36                    // panel leading dimension (doubles): conflict-free fragment reads
+#define BF_SETUP_RL_MAX_NP 736
+
+// c += A(32 x 4 ksteps, row-major, lda) * op(B); BKM = false: op(B) = B^T with B row-major 32 x K (ldb);
+// BKM = true: op(B) = B with B row-major K x 32 (ldb).  One k-step of operands is fetched ahead.
+template <bool BKM>
+__device__ __forceinline__ void rl_tile(double (&c)[4][4][2], const double* __restrict__ A, int lda,
+                                        const double* __restrict__ B, int ldb, int ksteps) {
+    const int lane = threadIdx.x & 31, r = lane >> 2, kk = lane & 3;
+    const double* ap = A + (size_t)r * lda + kk;
+    const double* bp = BKM ? B + (size_t)kk * ldb + r : B + (size_t)r * ldb + kk;
+    double a[4], b[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        a[t] = ap[(size_t)(8 * t) * lda];
+        b[t] = BKM ? bp[8 * t] : bp[(size_t)(8 * t) * ldb];
+    }
+    for (int ks = 0; ks < ksteps; ++ks) {
+        double an[4], bn[4];
+        if (ks + 1 < ksteps) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                an[t] = ap[(size_t)(8 * t) * lda + 4 * (ks + 1)];
+                bn[t] = BKM ? bp[(size_t)(4 * (ks + 1)) * ldb + 8 * t] : bp[(size_t)(8 * t) * ldb + 4 * (ks + 1)];
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) bf_dmma(c[t][u][0], c[t][u][1], a[t], b[u]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            a[t] = an[t];
+            b[t] = bn[t];
+        }
+    }
+}
+
+__device__ __forceinline__ void rl_zero(double (&c)[4][4][2]) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c[t][u][0] = c[t][u][1] = 0.0;
+}
+
+// lower Cholesky of the 32 x 32 block in Ld (one warp, lane = row); returns the first bad pivot + 1 or 0
+__device__ __forceinline__ int rl_factor_block(double (*Ld)[33], int lane) {
+    int bad = 0;
+    for (int j = 0; j < 32; ++j) {
+        const double djj = Ld[j][j];
+        if (!(djj > 0.0) && bad == 0) bad = j + 1;
+        const double dj = sqrt(djj);
+        __syncwarp();
+        if (lane == j) Ld[j][j] = dj;
+        if (lane > j) Ld[lane][j] = Ld[lane][j] / dj;
+        __syncwarp();
+        if (lane > j) {
+            const double lij = Ld[lane][j];
+            for (int cc = j + 1; cc <= lane; ++cc) Ld[lane][cc] = fma(-lij, Ld[cc][j], Ld[lane][cc]);
+        }
+        __syncwarp();
+    }
+    return bad;
+}
+
+// inverse of the lower-triangular block Ld into Li (one warp, lane = column of the inverse)
+__device__ __forceinline__ void rl_invert_block(const double (*Ld)[33], double (*Li)[33], int lane) {
+    double x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        double s = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int t = 0; t < i; ++t) s = fma(-Ld[i][t], x[t], s);          // x[t] = 0 for t < lane
+        x[i] = (i >= lane) ? s / Ld[i][i] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) Li[i][lane] = x[i];
+}
+
+__global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_cholesky_rl_kernel(int n, int np, double* __restrict__ Aall,
+                                                                          int32_t* __restrict__ info) {
+    extern __shared__ __align__(16) double rl_sm[];
+    double* panel = rl_sm;                                          // (np - 32) x BF_RL_PLD
+    double (*Ld)[33] = reinterpret_cast<double (*)[33]>(panel + (size_t)(np - 32) * BF_RL_PLD);
+    double (*Li)[33] = Ld + 32;
+    __shared__ int bad;
+    double* A = Aall + (size_t)blockIdx.x * np * np;
+    const int nb = np / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    for (int kb = 0; kb < nb; ++kb) {
+        const int r0 = 32 * kb;
+        // 1. diagonal block: factor and invert (warp 0)
+        if (warp == 0) {
+            for (int j = 0; j < 32; ++j) Ld[lane][j] = A[(size_t)(r0 + lane) * np + r0 + j];
+            __syncwarp();
+            const int b = rl_factor_block(Ld, lane);
+            if (b && lane == 0 && bad == 0) bad = r0 + b;
+            for (int j = 0; j < 32; ++j) {
+                if (j > lane) Ld[lane][j] = 0.0;
+                A[(size_t)(r0 + lane) * np + r0 + j] = Ld[lane][j];
+            }
+            __syncwarp();
+            rl_invert_block(Ld, Li, lane);
+        }
+        __syncthreads();
+        // 2. panel column: P_i = A[i, k] L_kk^-T for the row blocks below, kept in shared memory
+        for (int ib = kb + 1 + warp; ib < nb; ib += BF_RL_WARPS) {
+            double c[4][4][2];
+            rl_zero(c);
+            rl_tile<false>(c, A + (size_t)(32 * ib) * np + r0, np, &Li[0][0], 33, 8);
+            double* prow = panel + (size_t)(32 * (ib - kb - 1)) * BF_RL_PLD;
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int rr = 8 * t + (lane >> 2), cc = 8 * u + 2 * (lane & 3);
+                    const double2 v = make_double2(c[t][u][0], c[t][u][1]);
+                    *reinterpret_cast<double2*>(prow + (size_t)rr * BF_RL_PLD + cc) = v;
+                    *reinterpret_cast<double2*>(A + (size_t)(32 * ib + rr) * np + r0 + cc) = v;
+                }
+        }
+        __syncthreads();
+        // 3. trailing update: A[i, j] -= P_i P_j^T for kb < j <= i
+        const int m = nb - kb - 1;
+        const int ntiles = m * (m + 1) / 2;
+        for (int q = warp; q < ntiles; q += BF_RL_WARPS) {
+            int ii = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
+            while (ii * (ii + 1) / 2 > q) --ii;
+            while ((ii + 1) * (ii + 2) / 2 <= q) ++ii;
+            const int jj = q - ii * (ii + 1) / 2;
+            double* dst0 = A + (size_t)(32 * (kb + 1 + ii) + (lane >> 2)) * np + 32 * (kb + 1 + jj) + 2 * (lane & 3);
+            double2 old[4][4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) old[t][u] = *reinterpret_cast<double2*>(dst0 + (size_t)(8 * t) * np + 8 * u);
+            double c[4][4][2];
+            rl_zero(c);
+            rl_tile<false>(c, panel + (size_t)(32 * ii) * BF_RL_PLD, BF_RL_PLD, panel + (size_t)(32 * jj) * BF_RL_PLD,
+                           BF_RL_PLD, 8);
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    double2 v = old[t][u];
+                    v.x -= c[t][u][0];
+                    v.y -= c[t][u][1];
+                    *reinterpret_cast<double2*>(dst0 + (size_t)(8 * t) * np + 8 * u) = v;
+                }
+        }
+        __syncthreads();
+    }
+    // the strictly upper 32 x 32 blocks still hold K: clear them so the output is L
+    for (int e = threadIdx.x; e < np * (np / 2); e += BF_RL_THREADS) {
+        const int i = e / (np / 2), j2 = (e - i * (np / 2)) * 2;
+        if ((j2 >> 5) > (i >> 5)) *reinterpret_cast<double2*>(A + (size_t)i * np + j2) = make_double2(0.0, 0.0);
+    }
+    if (threadIdx.x == 0 && info) info[blockIdx.x] = bad;
+}
+
+__global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_factor_finish_rl_kernel(
+    int n, int np, const double* __restrict__ Lall, const double* __restrict__ y, long long y_stride,
+    double* __restrict__ Linv_all, double* __restrict__ packed_all, size_t packed_stride,
+    double* __restrict__ alpha_all) {
+    extern __shared__ __align__(16) double rl_sm[];
+    const int wld = np + 4;                                         // W row panel leading dimension
+    double* tvec = rl_sm;                                           // np
+    double* W = rl_sm + np;                                         // 32 x (np + 4)       (phase 2)
+    double (*Ld)[33] = reinterpret_cast<double (*)[33]>(W);         // per-warp 2 x 32 x 33 (phase 1, aliased)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int set = blockIdx.x;
+    const double* L = Lall + (size_t)set * np * np;
+    double* Linv = Linv_all + (size_t)set * np * np;
+    double* packed = packed_all + (size_t)set * packed_stride;
+    const int nb = np / 32;
+
+    // phase 1: inverses of the diagonal blocks; zero the blocks right of the diagonal
+    for (int kb = warp; kb < nb; kb += BF_RL_WARPS) {
+        const int r0 = 32 * kb;
+        double (*Lw)[33] = Ld + (size_t)warp * 64;
+        double (*Lo)[33] = Lw + 32;
+        for (int j = 0; j < 32; ++j) Lw[lane][j] = L[(size_t)(r0 + lane) * np + r0 + j];
+        __syncwarp();
+        rl_invert_block(Lw, Lo, lane);
+        __syncwarp();
+        for (int i = 0; i < 32; ++i) {
+            const double v = Lo[i][lane];
+            Linv[(size_t)(r0 + i) * np + r0 + lane] = v;
+            packed[bf_linv_elem_off(r0 + i, r0 + lane)] = v;
+        }
+        for (int jb = kb + 1; jb < nb; ++jb)
+            for (int i = 0; i < 32; ++i) Linv[(size_t)(r0 + i) * np + 32 * jb + lane] = 0.0;
+    }
+    __syncthreads();
+
+    // phase 2: block row I of the inverse
+    for (int I = 1; I < nb; ++I) {
+        // W[:, K] = Linv_II * L[I, K] for K < I (B operand k-major, straight from the row-major L)
+        for (int K = warp; K < I; K += BF_RL_WARPS) {
+            double c[4][4][2];
+            rl_zero(c);
+            rl_tile<true>(c, Linv + (size_t)(32 * I) * np + 32 * I, np, L + (size_t)(32 * I) * np + 32 * K, np, 8);
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int rr = 8 * t + (lane >> 2), cc = 32 * K + 8 * u + 2 * (lane & 3);
+                    *reinterpret_cast<double2*>(W + (size_t)rr * wld + cc) = make_double2(c[t][u][0], c[t][u][1]);
+                }
+        }
+        __syncthreads();
+        // Linv[I, J] = - sum_{K = J}^{I - 1} W[:, K] Linv[K, J]
+        for (int J = warp; J < I; J += BF_RL_WARPS) {
+            double c[4][4][2];
+            rl_zero(c);
+            rl_tile<true>(c, W + 32 * J, wld, Linv + (size_t)(32 * J) * np + 32 * J, np, 8 * (I - J));
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = 32 * I + 8 * t + (lane >> 2), j = 32 * J + 8 * u + 2 * (lane & 3);
+                    const double2 v = make_double2(-c[t][u][0], -c[t][u][1]);
+                    *reinterpret_cast<double2*>(Linv + (size_t)i * np + j) = v;
+                    packed[bf_linv_elem_off(i, j)] = v.x;
+                    packed[bf_linv_elem_off(i, j + 1)] = v.y;
+                }
+        }
+        __syncthreads();
+    }
+
+    // phase 3: alpha = Linv^T (Linv y)
+    if (alpha_all) {
+        const double* yv = y + (size_t)set * y_stride;
+        for (int i = threadIdx.x; i < np; i += BF_RL_THREADS) {
+            double s = 0.0;
+            if (i < n) {
+                const double* row = Linv + (size_t)i * np;
+                for (int j = 0; j <= i; ++j) s = fma(row[j], yv[j], s);
+            }
+            tvec[i] = s;
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < n; j += BF_RL_THREADS) {
+            double s = 0.0;
+            for (int i = j; i < n; ++i) s = fma(Linv[(size_t)i * np + j], tvec[i], s);
+            alpha_all[(size_t)set * n + j] = s;
+        }
+    }
+}
+
 // ---- batched Cholesky (left-looking, 32-wide panels, one CTA per matrix) ----------------------
 __global__ void __launch_bounds__(BF_THREADS) bf_cholesky_kernel(int n, int np, double* __restrict__ Aall,
                                                                  int32_t* __restrict__ info) {
@@ -175,7 +437,17 @@ extern "C" int bf_cholesky_batched(int n, int S, double* K_inout_L, int32_t* inf
     BF_CHECK_ARG(n > 0 && S >= 0 && K_inout_L, BF_ERR_ARG, "bf_cholesky_batched: bad argument");
     if (S == 0) return 0;
     const int np = bf_padded_n(n);
-    bf_cholesky_kernel<<<S, BF_THREADS, 0, (cudaStream_t)stream>>>(n, np, K_inout_L, info);
+    if (np <= BF_SETUP_RL_MAX_NP) {
+        const size_t smem = sizeof(double) * ((size_t)(np - 32) * BF_RL_PLD + 2 * 32 * 33);
+        cudaError_t e = cudaFuncSetAttribute(bf_cholesky_rl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            bf_set_error("bf_cholesky_batched: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        bf_cholesky_rl_kernel<<<S, BF_RL_THREADS, smem, (cudaStream_t)stream>>>(n, np, K_inout_L, info);
+    } else {
+        bf_cholesky_kernel<<<S, BF_THREADS, 0, (cudaStream_t)stream>>>(n, np, K_inout_L, info);
+    }
     BF_CHECK_LAUNCH("bf_cholesky_batched");
     return 0;
 }
@@ -325,6 +597,20 @@ extern "C" int bf_factor_finish(int n, int S, const double* L, const double* y, 
     BF_CHECK_ARG(!alpha || y, BF_ERR_ARG, "bf_factor_finish: alpha requested without y");
     if (S == 0) return 0;
     const int np = bf_padded_n(n);
+    if (np <= BF_SETUP_RL_MAX_NP) {
+        const size_t w_sz = (size_t)32 * (np + 4), scratch = (size_t)BF_RL_WARPS * 64 * 33;
+        const size_t smem_rl = sizeof(double) * (np + (w_sz > scratch ? w_sz : scratch));
+        cudaError_t e2 = cudaFuncSetAttribute(bf_factor_finish_rl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem_rl);
+        if (e2 != cudaSuccess) {
+            bf_set_error("bf_factor_finish: cudaFuncSetAttribute: %s", cudaGetErrorString(e2));
+            return (int)e2;
+        }
+        bf_factor_finish_rl_kernel<<<S, BF_RL_THREADS, smem_rl, (cudaStream_t)stream>>>(
+            n, np, L, y, y_stride, Linv, linv_packed, bf_linv_packed_doubles(n), alpha);
+        BF_CHECK_LAUNCH("bf_factor_finish");
+        return 0;
+    }
     const size_t smem = sizeof(double) * ((size_t)BF_WARPS * 32 * 33 + np);
     cudaError_t e = cudaFuncSetAttribute(bf_factor_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
