@@ -97,6 +97,20 @@ __device__ __forceinline__ void bf_tile_abt(double (&c)[4][4][2], const double* 
 //   update A[i, j] -= P_i P_j^T then runs with both operands in shared memory, up to 120 tiles
 //   spread over the warps;
 //   inverse (row by row): W = L_II^-1 L[I, 0:I], after which L^-1[I, J] = - sum_K W_IK L^-1[K, J].
+#ifdef BF_PROFILE_SETUP
+__device__ long long bf_prof_cycles[8];
+#define BF_PROF_MARK(slot)                                                        \
+    do {                                                                          \
+        __syncthreads();                                                          \
+        if (threadIdx.x == 0) {                                                   \
+            const long long now_ = clock64();                                     \
+            atomicAdd((unsigned long long*)&bf_prof_cycles[slot], (unsigned long long)(now_ - prof_t_)); \
+            prof_t_ = now_;                                                       \
+        }                                                                         \
+    } while (0)
+#else
+#define BF_PROF_MARK(slot)
+#endif
 #define BF_RL_WARPS 8
 #define BF_RL_THREADS (BF_RL_WARPS * 32)
 #define BF_RL_PLD 36                    // panel leading dimension (doubles): conflict-free fragment reads
@@ -107,33 +121,44 @@ __device__ __forceinline__ void bf_tile_abt(double (&c)[4][4][2], const double* 
 template <bool BKM>
 __device__ __forceinline__ void rl_tile(double (&c)[4][4][2], const double* __restrict__ A, int lda,
                                         const double* __restrict__ B, int ldb, int ksteps) {
+    // ksteps is a multiple of 4; operands of the NEXT group of 4 k-steps are in flight while the
+    // current group is multiplied (64 DMMAs cover an L2 round trip)
     const int lane = threadIdx.x & 31, r = lane >> 2, kk = lane & 3;
     const double* ap = A + (size_t)r * lda + kk;
     const double* bp = BKM ? B + (size_t)kk * ldb + r : B + (size_t)r * ldb + kk;
-    double a[4], b[4];
+    double a[4][4], b[4][4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        a[t] = ap[(size_t)(8 * t) * lda];
-        b[t] = BKM ? bp[8 * t] : bp[(size_t)(8 * t) * ldb];
-    }
-    for (int ks = 0; ks < ksteps; ++ks) {
-        double an[4], bn[4];
-        if (ks + 1 < ksteps) {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                an[t] = ap[(size_t)(8 * t) * lda + 4 * (ks + 1)];
-                bn[t] = BKM ? bp[(size_t)(4 * (ks + 1)) * ldb + 8 * t] : bp[(size_t)(8 * t) * ldb + 4 * (ks + 1)];
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-#pragma unroll
-            for (int u = 0; u < 4; ++u) bf_dmma(c[t][u][0], c[t][u][1], a[t], b[u]);
+    for (int h = 0; h < 4; ++h)
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            a[t] = an[t];
-            b[t] = bn[t];
+            a[h][t] = ap[(size_t)(8 * t) * lda + 4 * h];
+            b[h][t] = BKM ? bp[(size_t)(4 * h) * ldb + 8 * t] : bp[(size_t)(8 * t) * ldb + 4 * h];
         }
+    for (int ks = 0; ks < ksteps; ks += 4) {
+        double an[4][4], bn[4][4];
+        if (ks + 4 < ksteps) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    an[h][t] = ap[(size_t)(8 * t) * lda + 4 * (ks + 4 + h)];
+                    bn[h][t] = BKM ? bp[(size_t)(4 * (ks + 4 + h)) * ldb + 8 * t]
+                                   : bp[(size_t)(8 * t) * ldb + 4 * (ks + 4 + h)];
+                }
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) bf_dmma(c[t][u][0], c[t][u][1], a[h][t], b[h][u]);
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                a[h][t] = an[h][t];
+                b[h][t] = bn[h][t];
+            }
     }
 }
 
@@ -144,38 +169,92 @@ __device__ __forceinline__ void rl_zero(double (&c)[4][4][2]) {
         for (int u = 0; u < 4; ++u) c[t][u][0] = c[t][u][1] = 0.0;
 }
 
-// lower Cholesky of the 32 x 32 block in Ld (one warp, lane = row); returns the first bad pivot + 1 or 0
-__device__ __forceinline__ int rl_factor_block(double (*Ld)[33], int lane) {
-    int bad = 0;
-    for (int j = 0; j < 32; ++j) {
-        const double djj = Ld[j][j];
-        if (!(djj > 0.0) && bad == 0) bad = j + 1;
-        const double dj = sqrt(djj);
-        __syncwarp();
-        if (lane == j) Ld[j][j] = dj;
-        if (lane > j) Ld[lane][j] = Ld[lane][j] / dj;
-        __syncwarp();
-        if (lane > j) {
-            const double lij = Ld[lane][j];
-            for (int cc = j + 1; cc <= lane; ++cc) Ld[lane][cc] = fma(-lij, Ld[cc][j], Ld[lane][cc]);
+// lower Cholesky of the 32 x 32 block in Ld (one warp).  Lane = row, the row lives in registers and
+// column j of the factor is broadcast with shuffles: ~1500 instructions instead of ~1000 dependent
+// shared-memory round trips.  Template recursion keeps every register index a compile-time constant.
+template <int J>
+__device__ __forceinline__ void rl_factor_step(double (&row)[32], int lane, int& bad, double& my_rdiag) {
+    if constexpr (J < 32) {
+        const double djj = __shfl_sync(0xffffffffu, row[J], J);
+        if (!(djj > 0.0) && bad == 0) bad = J + 1;
+        // one reciprocal square root per pivot (Newton-refined, < 1 ulp) instead of a square root and 31
+        // divisions on the critical path of a single warp
+        double rinv = rsqrt(djj);
+        rinv = fma(rinv * 0.5, fma(-djj * rinv, rinv, 1.0), rinv);
+        if (lane == J) {
+            row[J] = djj * rinv;
+            my_rdiag = rinv;
         }
-        __syncwarp();
+        if (lane > J) row[J] = row[J] * rinv;
+        const double lij = row[J];
+#pragma unroll
+        for (int cc = J + 1; cc < 32; ++cc) {
+            const double lcj = __shfl_sync(0xffffffffu, lij, cc);           // L[cc][J]
+            if (lane >= cc) row[cc] = fma(-lij, lcj, row[cc]);
+        }
+        rl_factor_step<J + 1>(row, lane, bad, my_rdiag);
     }
+}
+
+// Returns the first bad pivot + 1 or 0; Ld receives L (zeros above the diagonal), rdiag[j] = 1 / L[j][j].
+__device__ __forceinline__ int rl_factor_block(double (*Ld)[33], double* rdiag, int lane) {
+    double row[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) row[j] = Ld[lane][j];
+    int bad = 0;
+    double my_rdiag = 0.0;
+    rl_factor_step<0>(row, lane, bad, my_rdiag);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) Ld[lane][j] = (j <= lane) ? row[j] : 0.0;
+    rdiag[lane] = my_rdiag;
+    __syncwarp();
     return bad;
 }
 
-// inverse of the lower-triangular block Ld into Li (one warp, lane = column of the inverse)
-__device__ __forceinline__ void rl_invert_block(const double (*Ld)[33], double (*Li)[33], int lane) {
+// inverse of the lower-triangular block Ld into Li (one warp, lane = column of the inverse); four
+// partial sums per row shorten the dependent FMA chain.  rdiag = reciprocal diagonal, or NULL.
+__device__ __forceinline__ void rl_invert_block(const double (*Ld)[33], const double* rdiag, double (*Li)[33],
+                                                int lane) {
     double x[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-        double s = (i == lane) ? 1.0 : 0.0;
+        double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-        for (int t = 0; t < i; ++t) s = fma(-Ld[i][t], x[t], s);          // x[t] = 0 for t < lane
-        x[i] = (i >= lane) ? s / Ld[i][i] : 0.0;
+        for (int t = 0; t + 3 < i; t += 4) {
+            s0 = fma(-Ld[i][t], x[t], s0);                                  // x[t] = 0 for t < lane
+            s1 = fma(-Ld[i][t + 1], x[t + 1], s1);
+            s2 = fma(-Ld[i][t + 2], x[t + 2], s2);
+            s3 = fma(-Ld[i][t + 3], x[t + 3], s3);
+        }
+#pragma unroll
+        for (int t = (i / 4) * 4; t < i; ++t) s0 = fma(-Ld[i][t], x[t], s0);
+        const double s = (s0 + s1) + (s2 + s3);
+        const double v = rdiag ? s * rdiag[i] : s / Ld[i][i];
+        x[i] = (i >= lane) ? v : 0.0;
     }
 #pragma unroll
     for (int i = 0; i < 32; ++i) Li[i][lane] = x[i];
+}
+
+// c += A * B^T with both operands in shared memory (32 x 4 ksteps each, leading dimension ld)
+__device__ __forceinline__ void rl_tile_smem(double (&c)[4][4][2], const double* __restrict__ A,
+                                             const double* __restrict__ B, int ld, int ksteps) {
+    const int lane = threadIdx.x & 31, r = lane >> 2, kk = lane & 3;
+    const double* ap = A + (size_t)r * ld + kk;
+    const double* bp = B + (size_t)r * ld + kk;
+#pragma unroll 2
+    for (int ks = 0; ks < ksteps; ++ks) {
+        double a[4], b[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            a[t] = ap[(size_t)(8 * t) * ld + 4 * ks];
+            b[t] = bp[(size_t)(8 * t) * ld + 4 * ks];
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) bf_dmma(c[t][u][0], c[t][u][1], a[t], b[u]);
+    }
 }
 
 __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_cholesky_rl_kernel(int n, int np, double* __restrict__ Aall,
@@ -185,27 +264,30 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_cholesky_rl_kernel(int n,
     double (*Ld)[33] = reinterpret_cast<double (*)[33]>(panel + (size_t)(np - 32) * BF_RL_PLD);
     double (*Li)[33] = Ld + 32;
     __shared__ int bad;
+    __shared__ double rdiag[32];
     double* A = Aall + (size_t)blockIdx.x * np * np;
     const int nb = np / 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) bad = 0;
     __syncthreads();
+#ifdef BF_PROFILE_SETUP
+    long long prof_t_ = clock64();
+#endif
     for (int kb = 0; kb < nb; ++kb) {
         const int r0 = 32 * kb;
         // 1. diagonal block: factor and invert (warp 0)
         if (warp == 0) {
-            for (int j = 0; j < 32; ++j) Ld[lane][j] = A[(size_t)(r0 + lane) * np + r0 + j];
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) Ld[j][lane] = A[(size_t)(r0 + j) * np + r0 + lane];   // coalesced rows
             __syncwarp();
-            const int b = rl_factor_block(Ld, lane);
+            const int b = rl_factor_block(Ld, rdiag, lane);
             if (b && lane == 0 && bad == 0) bad = r0 + b;
-            for (int j = 0; j < 32; ++j) {
-                if (j > lane) Ld[lane][j] = 0.0;
-                A[(size_t)(r0 + lane) * np + r0 + j] = Ld[lane][j];
-            }
-            __syncwarp();
-            rl_invert_block(Ld, Li, lane);
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) A[(size_t)(r0 + j) * np + r0 + lane] = Ld[j][lane];
+            rl_invert_block(Ld, rdiag, Li, lane);
         }
         __syncthreads();
+        BF_PROF_MARK(0);
         // 2. panel column: P_i = A[i, k] L_kk^-T for the row blocks below, kept in shared memory
         for (int ib = kb + 1 + warp; ib < nb; ib += BF_RL_WARPS) {
             double c[4][4][2];
@@ -223,7 +305,9 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_cholesky_rl_kernel(int n,
                 }
         }
         __syncthreads();
-        // 3. trailing update: A[i, j] -= P_i P_j^T for kb < j <= i
+        BF_PROF_MARK(1);
+        // 3. trailing update: A[i, j] -= P_i P_j^T for kb < j <= i (both operands in shared memory; the
+        //    old values are requested first so their L2 round trip overlaps the 64 DMMAs)
         const int m = nb - kb - 1;
         const int ntiles = m * (m + 1) / 2;
         for (int q = warp; q < ntiles; q += BF_RL_WARPS) {
@@ -239,8 +323,7 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_cholesky_rl_kernel(int n,
                 for (int u = 0; u < 4; ++u) old[t][u] = *reinterpret_cast<double2*>(dst0 + (size_t)(8 * t) * np + 8 * u);
             double c[4][4][2];
             rl_zero(c);
-            rl_tile<false>(c, panel + (size_t)(32 * ii) * BF_RL_PLD, BF_RL_PLD, panel + (size_t)(32 * jj) * BF_RL_PLD,
-                           BF_RL_PLD, 8);
+            rl_tile_smem(c, panel + (size_t)(32 * ii) * BF_RL_PLD, panel + (size_t)(32 * jj) * BF_RL_PLD, BF_RL_PLD, 8);
 #pragma unroll
             for (int t = 0; t < 4; ++t)
 #pragma unroll
@@ -252,6 +335,7 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_cholesky_rl_kernel(int n,
                 }
         }
         __syncthreads();
+        BF_PROF_MARK(2);
     }
     // the strictly upper 32 x 32 blocks still hold K: clear them so the output is L
     for (int e = threadIdx.x; e < np * (np / 2); e += BF_RL_THREADS) {
@@ -282,9 +366,10 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_factor_finish_rl_kernel(
         const int r0 = 32 * kb;
         double (*Lw)[33] = Ld + (size_t)warp * 64;
         double (*Lo)[33] = Lw + 32;
-        for (int j = 0; j < 32; ++j) Lw[lane][j] = L[(size_t)(r0 + lane) * np + r0 + j];
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) Lw[j][lane] = L[(size_t)(r0 + j) * np + r0 + lane];       // coalesced rows
         __syncwarp();
-        rl_invert_block(Lw, Lo, lane);
+        rl_invert_block(Lw, nullptr, Lo, lane);
         __syncwarp();
         for (int i = 0; i < 32; ++i) {
             const double v = Lo[i][lane];
@@ -334,13 +419,15 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_factor_finish_rl_kernel(
     // phase 3: alpha = Linv^T (Linv y)
     if (alpha_all) {
         const double* yv = y + (size_t)set * y_stride;
-        for (int i = threadIdx.x; i < np; i += BF_RL_THREADS) {
+        for (int i = warp; i < np; i += BF_RL_WARPS) {       // warp per row: coalesced, fixed-order lane tree
             double s = 0.0;
             if (i < n) {
                 const double* row = Linv + (size_t)i * np;
-                for (int j = 0; j <= i; ++j) s = fma(row[j], yv[j], s);
+                for (int j = lane; j <= i; j += 32) s = fma(row[j], yv[j], s);
             }
-            tvec[i] = s;
+#pragma unroll
+            for (int mm = 16; mm > 0; mm >>= 1) s += __shfl_xor_sync(0xffffffffu, s, mm);
+            if (lane == 0) tvec[i] = s;
         }
         __syncthreads();
         for (int j = threadIdx.x; j < n; j += BF_RL_THREADS) {
