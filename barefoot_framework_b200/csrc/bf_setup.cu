@@ -360,6 +360,9 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_factor_finish_rl_kernel(
     double* Linv = Linv_all + (size_t)set * np * np;
     double* packed = packed_all + (size_t)set * packed_stride;
     const int nb = np / 32;
+#ifdef BF_PROFILE_SETUP
+    long long prof_t_ = clock64();
+#endif
 
     // phase 1: inverses of the diagonal blocks; zero the blocks right of the diagonal
     for (int kb = warp; kb < nb; kb += BF_RL_WARPS) {
@@ -380,6 +383,7 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_factor_finish_rl_kernel(
             for (int i = 0; i < 32; ++i) Linv[(size_t)(r0 + i) * np + 32 * jb + lane] = 0.0;
     }
     __syncthreads();
+    BF_PROF_MARK(3);
 
     // phase 2: block row I of the inverse
     for (int I = 1; I < nb; ++I) {
@@ -397,6 +401,7 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_factor_finish_rl_kernel(
                 }
         }
         __syncthreads();
+        BF_PROF_MARK(4);
         // Linv[I, J] = - sum_{K = J}^{I - 1} W[:, K] Linv[K, J]
         for (int J = warp; J < I; J += BF_RL_WARPS) {
             double c[4][4][2];
@@ -414,6 +419,7 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_factor_finish_rl_kernel(
                 }
         }
         __syncthreads();
+        BF_PROF_MARK(5);
     }
 
     // phase 3: alpha = Linv^T (Linv y)
@@ -436,6 +442,7 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_factor_finish_rl_kernel(
             alpha_all[(size_t)set * n + j] = s;
         }
     }
+    BF_PROF_MARK(6);
 }
 
 // ---- batched Cholesky (left-looking, 32-wide panels, one CTA per matrix) ----------------------

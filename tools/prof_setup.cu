@@ -14,6 +14,9 @@ int main() {
     double *dX, *dil, *damp, *dyerr, *dK; int* dinfo;
     cudaMalloc(&dX, X.size() * 8); cudaMalloc(&dil, d * 8); cudaMalloc(&damp, 8); cudaMalloc(&dyerr, 8);
     cudaMalloc(&dK, (size_t)np * np * 8); cudaMalloc(&dinfo, 4);
+    double *dy, *dLinv, *dpacked, *dalpha;
+    cudaMalloc(&dy, np * 8); cudaMemset(dy, 0, np * 8); cudaMalloc(&dLinv, (size_t)np * np * 8);
+    cudaMalloc(&dpacked, bf_linv_packed_doubles(n) * 8); cudaMalloc(&dalpha, np * 8);
     cudaMemcpy(dX, X.data(), X.size() * 8, cudaMemcpyHostToDevice); cudaMemcpy(dil, il.data(), d * 8, cudaMemcpyHostToDevice);
     cudaMemcpy(damp, amp.data(), 8, cudaMemcpyHostToDevice); cudaMemcpy(dyerr, yerr.data(), 8, cudaMemcpyHostToDevice);
     for (int rep = 0; rep < 3; ++rep) {
@@ -29,6 +32,14 @@ int main() {
         int info; cudaMemcpy(&info, dinfo, 4, cudaMemcpyDeviceToHost);
         printf("rc %d info %d  cholesky %.1f us : diag %lld panel %lld trailing %lld cycles (%s)\n", rc, info, ms * 1e3, prof[0], prof[1],
                prof[2], cudaGetErrorString(cudaGetLastError()));
+        cudaMemcpyToSymbol(bf_prof_cycles, zero, sizeof(zero));
+        cudaEventRecord(e0);
+        rc = bf_factor_finish(n, 1, dK, dy, 0, dLinv, dpacked, dalpha, nullptr);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaMemcpyFromSymbol(prof, bf_prof_cycles, sizeof(prof));
+        printf("rc %d finish %.1f us : diag-inverses %lld W %lld rows %lld alpha %lld cycles (%s)\n", rc, ms * 1e3, prof[3], prof[4],
+               prof[5], prof[6], cudaGetErrorString(cudaGetLastError()));
     }
     return 0;
 }
