@@ -20,12 +20,13 @@ __global__ void __launch_bounds__(256) bf_cross_matrix_kernel(int kern, long lon
     const long long a0 = (long long)blockIdx.y * 32;
     const int j0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int e = threadIdx.x; e < 32 * d; e += 256) {
+    if (threadIdx.x < d) w_s[threadIdx.x] = bf_metric_scale(kern, inv_l2[threadIdx.x]);
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * d; e += 256) {       // pre-scaled coordinates
         const int r = e / d, c = e - r * d;
-        xa_s[r][c] = (a0 + r < A) ? Xa[(size_t)(a0 + r) * d + c] : 0.0;
-        xj_s[r][c] = (j0 + r < n) ? X[(size_t)(j0 + r) * d + c] : 0.0;
+        xa_s[r][c] = (a0 + r < A) ? Xa[(size_t)(a0 + r) * d + c] * w_s[c] : 0.0;
+        xj_s[r][c] = (j0 + r < n) ? X[(size_t)(j0 + r) * d + c] * w_s[c] : 0.0;
     }
-    if (threadIdx.x < d) w_s[threadIdx.x] = inv_l2[threadIdx.x];
     __syncthreads();
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
@@ -34,12 +35,12 @@ __global__ void __launch_bounds__(256) bf_cross_matrix_kernel(int kern, long lon
         const int j = j0 + tx;
         double v = 0.0;
         if (a < A && j < n) {
-            double r2 = 0.0;
+            double q = 0.0;
             for (int c = 0; c < d; ++c) {
                 const double df = xa_s[r][c] - xj_s[tx][c];
-                r2 = fma(df * df, w_s[c], r2);
+                q = fma(df, df, q);
             }
-            v = amp * bf_radial(kern, r2);
+            v = amp * bf_radial_q(kern, q, bf_exp_tab_g);
         }
         Ks[(size_t)a * np + j] = v;
     }
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(256) bf_cov_kernel(int kern, long long A, long
         for (int u = 0; u < 4; ++u) c[t][u][0] = c[t][u][1] = 0.0;
     cov_tile_abt(c, Vta + (size_t)a0 * np, Vtb + (size_t)b0 * np, np, np / 4);
     double w[BF_MAX_DIM];
-    for (int k = 0; k < d; ++k) w[k] = inv_l2[k];
+    for (int k = 0; k < d; ++k) w[k] = bf_metric_scale(kern, inv_l2[k]);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const long long a = a0 + 8 * t + (lane >> 2);
@@ -148,12 +149,12 @@ __global__ void __launch_bounds__(256) bf_cov_kernel(int kern, long long A, long
             for (int q = 0; q < 2; ++q) {
                 const long long b = b0 + 8 * u + 2 * (lane & 3) + q;
                 if (b >= B) continue;
-                double r2 = 0.0;
+                double qq = 0.0;
                 for (int k = 0; k < d; ++k) {
-                    const double df = Xa[(size_t)a * d + k] - Xb[(size_t)b * d + k];
-                    r2 = fma(df * df, w[k], r2);
+                    const double df = Xa[(size_t)a * d + k] * w[k] - Xb[(size_t)b * d + k] * w[k];
+                    qq = fma(df, df, qq);
                 }
-                C[(size_t)a * ldc + b] = amp * bf_radial(kern, r2) - c[t][u][q];
+                C[(size_t)a * ldc + b] = amp * bf_radial_q(kern, qq, bf_exp_tab_g) - c[t][u][q];
             }
     }
 }

@@ -52,7 +52,7 @@ __device__ __forceinline__ void gen_tile(const PostParams& p, const double* __re
     const int kk = lane & 3, nn = lane >> 2;
     double w[DR];
 #pragma unroll
-    for (int a = 0; a < DR; ++a) w[a] = a < dd ? 0.5 * w_s[a] : 0.0;     // exact: h2 = r2 / 2
+    for (int a = 0; a < DR; ++a) w[a] = a < dd ? w_s[a] : 0.0;           // metric scale (bf_metric_scale)
     const double* xc = xs_s + nn;            // this lane's candidates: xc[a * NT + 8 * at]
     double macc[NTA];
 #pragma unroll
@@ -69,7 +69,7 @@ __device__ __forceinline__ void gen_tile(const PostParams& p, const double* __re
             const int j = 4 * (g0 + h * nwarps) + kk;
             const bool valid = (g0 + h * nwarps) < ng && j < p.n;
 #pragma unroll
-            for (int a = 0; a < DR; ++a) xj[h][a] = (valid && a < dd) ? __ldg(p.X + (size_t)j * dd + a) : 0.0;
+            for (int a = 0; a < DR; ++a) xj[h][a] = (valid && a < dd) ? __ldg(p.X + (size_t)j * dd + a) * w[a] : 0.0;
             aj[h] = valid ? __ldg(alpha + j) : 0.0;
         }
         double v[G][NTA];
@@ -77,15 +77,15 @@ __device__ __forceinline__ void gen_tile(const PostParams& p, const double* __re
         for (int h = 0; h < G; ++h)
 #pragma unroll
             for (int at = 0; at < NTA; ++at) {
-                double h2 = 0.0;
+                double q = 0.0;
 #pragma unroll
                 for (int a = 0; a < DR; ++a) {
                     if (a < dd) {
-                        const double df = xc[a * NT + 8 * at] - xj[h][a];
-                        h2 = fma(df * df, w[a], h2);
+                        const double df = xc[a * NT + 8 * at] - xj[h][a];      // both pre-scaled
+                        q = fma(df, df, q);
                     }
                 }
-                v[h][at] = amp * bf_radial_half(p.kern, h2, tab);
+                v[h][at] = amp * bf_radial_q(p.kern, q, tab);
             }
 #pragma unroll
         for (int h = 0; h < G; ++h) {
@@ -251,14 +251,15 @@ __global__ void __launch_bounds__(BF_THREADS, MINB) bf_posterior_kernel(PostPara
     const long long c_base = (long long)tile * NT;
     const double amp = p.amp[hp];
 
-    for (int e = threadIdx.x; e < dd * NT; e += BF_THREADS) {
+    for (int e = threadIdx.x; e < BF_WARPS * NT; e += BF_THREADS) spart[e] = 0.0;
+    if (threadIdx.x < dd) w_s[threadIdx.x] = bf_metric_scale(p.kern, p.inv_l2[(size_t)hp * dd + threadIdx.x]);
+    if (threadIdx.x < BF_EXP_TAB_N) tab_s[threadIdx.x] = bf_exp_tab_g[threadIdx.x];
+    __syncthreads();
+    for (int e = threadIdx.x; e < dd * NT; e += BF_THREADS) {        // candidates, pre-scaled by the metric
         const int a = e / NT, c = e - a * NT;
         const long long gi = c_base + c;
-        xs_s[e] = gi < p.N ? p.Xs[gi * dd + a] : 0.0;
+        xs_s[e] = gi < p.N ? p.Xs[gi * dd + a] * w_s[a] : 0.0;
     }
-    for (int e = threadIdx.x; e < BF_WARPS * NT; e += BF_THREADS) spart[e] = 0.0;
-    if (threadIdx.x < dd) w_s[threadIdx.x] = p.inv_l2[(size_t)hp * dd + threadIdx.x];
-    if (threadIdx.x < BF_EXP_TAB_N) tab_s[threadIdx.x] = bf_exp_tab_g[threadIdx.x];
     __syncthreads();
 
     gen_tile<D, NTA>(p, w_s, xs_s, Bt, mpart, p.alpha + (size_t)set * p.n, amp, tab_s, threadIdx.x >> 5);
@@ -403,8 +404,9 @@ __global__ void __launch_bounds__(BF_DUAL_THREADS, 1) bf_posterior_dual_kernel(P
     const double sh = p.shift ? p.shift[set] : 0.0;
 
     for (int e = gtid; e < BF_WARPS * NT; e += BF_THREADS) spart[e] = 0.0;   // idle-queue slots stay 0
-    if (threadIdx.x < dd) w_s[threadIdx.x] = p.inv_l2[(size_t)hp * dd + threadIdx.x];
+    if (threadIdx.x < dd) w_s[threadIdx.x] = bf_metric_scale(p.kern, p.inv_l2[(size_t)hp * dd + threadIdx.x]);
     if (threadIdx.x < BF_EXP_TAB_N) tab_s[threadIdx.x] = bf_exp_tab_g[threadIdx.x];
+    __syncthreads();
 
     BfBest best[3];
 #pragma unroll
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(BF_DUAL_THREADS, 1) bf_posterior_dual_kernel(P
         for (int e = gtid; e < dd * NT; e += BF_THREADS) {
             const int a = e / NT, c = e - a * NT;
             const long long gi = c_base + c;
-            xs_s[e] = (active && gi < p.N) ? p.Xs[gi * dd + a] : 0.0;
+            xs_s[e] = (active && gi < p.N) ? p.Xs[gi * dd + a] * w_s[a] : 0.0;      // pre-scaled by the metric
         }
         __syncthreads();     // also orders the previous phase C before mpart / spart are rewritten
         if (active && !(p.debug_skip & 2)) gen_tile<D, NTA>(p, w_s, xs_s, Bt, mpart, alpha, amp, tab_s, gw);

@@ -17,12 +17,13 @@ __global__ void __launch_bounds__(256) bf_kernel_matrix_kernel(
     const int hp = set_hp ? set_hp[set] : set;
     const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int e = threadIdx.x; e < 32 * d; e += 256) {
+    if (threadIdx.x < d) w_s[threadIdx.x] = bf_metric_scale(kern, inv_l2[(size_t)hp * d + threadIdx.x]);
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * d; e += 256) {       // pre-scaled coordinates
         const int r = e / d, a = e - r * d;
-        xi_s[r][a] = (i0 + r < n) ? X[(size_t)(i0 + r) * d + a] : 0.0;
-        xj_s[r][a] = (j0 + r < n) ? X[(size_t)(j0 + r) * d + a] : 0.0;
+        xi_s[r][a] = (i0 + r < n) ? X[(size_t)(i0 + r) * d + a] * w_s[a] : 0.0;
+        xj_s[r][a] = (j0 + r < n) ? X[(size_t)(j0 + r) * d + a] * w_s[a] : 0.0;
     }
-    if (threadIdx.x < d) w_s[threadIdx.x] = inv_l2[(size_t)hp * d + threadIdx.x];
     __syncthreads();
     const double am = amp[hp];
     double* Kset = K + (size_t)set * np * np;
@@ -32,12 +33,12 @@ __global__ void __launch_bounds__(256) bf_kernel_matrix_kernel(
         const int i = i0 + r, j = j0 + tx;
         double v;
         if (i < n && j < n) {
-            double r2 = 0.0;
+            double q = 0.0;
             for (int a = 0; a < d; ++a) {
                 const double df = xi_s[r][a] - xj_s[tx][a];
-                r2 = fma(df * df, w_s[a], r2);
+                q = fma(df, df, q);
             }
-            v = am * bf_radial(kern, r2);
+            v = am * bf_radial_q(kern, q, bf_exp_tab_g);
             if (i == j) {
                 const double e = yerr_n == 1 ? yerr[0] : yerr[(size_t)set * yerr_stride + i];
                 const double s = sqrt(e * e + BF_TINY);   // george folds the jitter into yerr
