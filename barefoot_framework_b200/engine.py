@@ -134,12 +134,16 @@ def posterior_sweep(f, Xs, scale=None, shift=None, want_mu=False, want_var=False
     Xs [N, d], with the de-normalisation of predict_fused_GP / predict_low_order
     (reificationFusion.py:189-206) and the elementwise acquisitions fused in."""
     dev = device()
-    Xs = to_dev(Xs).reshape(len(Xs), -1)
+    Xs = to_dev(Xs)
+    Xs = Xs.reshape(Xs.shape[0], f.d)
     N = Xs.shape[0]
-    assert Xs.shape[1] == f.d
     lib = _lib.load()
     out = SweepResult()
     S = f.S
+    if N == 0:                  # empty candidate batch: nothing to launch (the reference's np.max would raise)
+        out.mu = torch.empty((S, 0), dtype=F64, device=dev) if want_mu else None
+        out.var = torch.empty((S, 0), dtype=F64, device=dev) if want_var else None
+        return out
     if want_mu:
         out.mu = torch.empty((S, N), dtype=F64, device=dev)
     if want_var:

@@ -270,3 +270,66 @@ def test_kmedoids_matches_oracle(eng, N, f, k):
     np.testing.assert_array_equal(med, km.medoid_indices_)
     np.testing.assert_array_equal(labels, km.labels_)
     assert n_iter == km.n_iter_
+
+
+@pytest.mark.parametrize("kern", ["SE", "M52"])
+@pytest.mark.parametrize("n,d,N", [(40, 10, 300), (300, 16, 700), (64, 9, 49), (900, 12, 100)])
+def test_posterior_high_dimensional_inputs(eng, kern, n, d, N):
+    """nDim 9..16 runs the run-time-dimension instantiation of the generators."""
+    rng = np.random.default_rng(n * 3 + d)
+    X, y, Xs = make_problem(rng, n, d, N)
+    l = rng.uniform(0.5, 1.5, size=(2, d))
+    sf = rng.uniform(0.5, 3.0, size=2)
+    f = eng.build_factors(kern, X, y, l ** 2, sf, 0.05)
+    res = eng.posterior_sweep(f, Xs, want_mu=True, want_var=True, acq_mask=15, curr_max=0.3, kt=0.5)
+    mu, var = res.mu.cpu().numpy(), res.var.cpu().numpy()
+    bi = res.best_idx.cpu().numpy()
+    for h in range(2):
+        g = fast.GP(X, y, l[h], sf[h], 0.05, d, kern)
+        mref, vref = g.predict_var(Xs)
+        assert np.abs(mu[h] - mref).max() <= REL * max(1.0, np.abs(mref).max())
+        assert np.abs(var[h] - vref).max() <= REL * sf[h] / d
+        assert bi[h, 3] == int(np.argmax(mu[h]))
+
+
+def test_edge_sizes(eng):
+    """One training point, one candidate, candidate counts around the tile size, an empty candidate set."""
+    rng = np.random.default_rng(0)
+    X = rng.uniform(size=(1, 2))
+    f = eng.build_factors("SE", X, np.array([0.7]), [[0.3 ** 2, 0.4 ** 2]], [1.5], 0.05)
+    g = fast.GP(X, np.array([0.7]), [0.3, 0.4], 1.5, 0.05, 2, "SE")
+    for N in (1, 23, 24, 25, 47, 48, 49, 96):
+        Xs = rng.uniform(size=(N, 2))
+        res = eng.posterior_sweep(f, Xs, want_mu=True, want_var=True, acq_mask=15, curr_max=0.1, kt=0.3)
+        mref, vref = g.predict_var(Xs)
+        np.testing.assert_allclose(res.mu[0].cpu().numpy(), mref, rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(res.var[0].cpu().numpy(), vref, rtol=1e-10, atol=1e-12)
+        assert int(res.best_idx[0, 3]) == int(np.argmax(mref))
+    from barefoot_framework_b200 import _lib
+    lib = _lib.load()
+    assert lib.bf_gp_posterior(0, 0, 1, 2, 1, None, None, None, None, None, None, None, None, None, None, None,
+                               0, 0, 0.0, 0.0, 0.0, None, None, None) != 0      # null inputs are rejected ...
+    assert b"null input" in lib.bf_last_error()
+    empty = eng.posterior_sweep(f, np.zeros((0, 2)), want_mu=True)               # ... an empty batch is a no-op
+    assert empty.mu.shape == (1, 0)
+
+
+def test_many_sets_share_training_inputs(eng):
+    """S = 300 sets with per-set targets and noise through a set -> hyper-parameter map (the ROM-stage shape)."""
+    rng = np.random.default_rng(4)
+    n, d, N, H, G = 20, 3, 60, 5, 60
+    X, _, Xs = make_problem(rng, n, d, N)
+    Y = rng.normal(size=(G * H, n))
+    E = rng.uniform(0.05, 0.3, size=(G * H, n))
+    l = rng.uniform(0.3, 0.9, size=(H, d))
+    sf = rng.uniform(0.5, 2.0, size=H)
+    set_hp = np.tile(np.arange(H, dtype=np.int32), G)
+    f = eng.build_factors("M32", X, Y, l ** 2, sf, E, set_hp=set_hp)
+    res = eng.posterior_sweep(f, Xs, want_mu=True, want_var=True)
+    mu, var = res.mu.cpu().numpy(), res.var.cpu().numpy()
+    for s in rng.choice(G * H, size=12, replace=False):
+        h = int(set_hp[s])
+        g = fast.GP(X, Y[s], l[h], sf[h], E[s], d, "M32")
+        mref, vref = g.predict_var(Xs)
+        assert np.abs(mu[s] - mref).max() <= REL * max(1.0, np.abs(mref).max())
+        assert np.abs(var[s] - vref).max() <= REL * sf[h] / d
