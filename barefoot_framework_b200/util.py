@@ -294,6 +294,32 @@ def batch_acquisition_batch(modelGP, hp_sets, x_test, curr_max, acqFunc, iterati
     return r[name]
 
 
+def batch_acquisition_multi(modelGP, hp_sets, x_test, curr_max, names=("EI", "PI", "UCB"), iteration=1, xi=0.01,
+                            return_device=False):
+    """Several elementwise acquisitions of the batch-only work item (util.py:913-1129) from ONE posterior
+    sweep: GP set-up for every hyper-parameter set, posterior over x_test (host array, pinned host tensor or
+    device tensor), then every requested acquisition fused into the epilogue.  Returns
+    {name: (values [H], indices [H])} as host arrays, or device tensors with return_device."""
+    hp = np.atleast_2d(np.asarray(hp_sets, dtype=np.float64))
+    x = np.asarray(modelGP.x_train, dtype=np.float64)
+    x = x.reshape(x.shape[0], -1)
+    y = np.asarray(modelGP.y_train, dtype=np.float64) - float(modelGP.mean)
+    f = engine.build_factors(modelGP.kern, x, y, hp[:, 1:], hp[:, 0], modelGP.sigma_n, ndim=modelGP.n_dim)
+    mask = 0
+    for nm in names:
+        mask |= ACQ_BITS[nm]
+    shift = None
+    if modelGP.mean:
+        shift = torch.full((f.S,), float(modelGP.mean), dtype=engine.F64, device=f.X.device)
+    res = engine.posterior_sweep(f, x_test, None if shift is None else torch.ones_like(shift), shift, acq_mask=mask,
+                                 spread_is_sqrt=False, curr_max=curr_max, xi=xi,
+                                 kt=engine.ucb_kt(f.d, iteration) if "UCB" in names else 0.0)
+    if return_device:
+        return {nm: (res.best_val[:, _SLOTS[nm]], res.best_idx[:, _SLOTS[nm]]) for nm in names}
+    bv, bi = res.best_val.cpu().numpy(), res.best_idx.cpu().numpy()
+    return {nm: (bv[:, _SLOTS[nm]].copy(), bi[:, _SLOTS[nm]].copy()) for nm in names}
+
+
 def batchAcquisitionFunc(param):
     """util.py:913-1129 (single-objective branch) with the reference's work-item signature."""
     with open("data/parameterSets/parameterSet{}".format(param[1]), 'rb') as fh:

@@ -81,14 +81,16 @@ def cpu_step(X, y, hp, sn, curr_max, Xs):
     return out
 
 
-def cpu_throughput(steps, warmup, sample=CPU_SAMPLE):
+def cpu_throughput(steps, warmup, sample=CPU_SAMPLE, want_result=False):
     X, y, hp, sn, curr_max, batches = make_workload(0, 1, sample)
     for _ in range(warmup):
         cpu_step(X, y, hp, sn, curr_max, batches[0][: max(1000, sample // 10)])
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_step(X, y, hp, sn, curr_max, batches[0])
+        out = cpu_step(X, y, hp, sn, curr_max, batches[0])
     dt = time.perf_counter() - t0
+    if want_result:
+        return steps * sample / dt, dt / steps, (X, y, hp, sn, curr_max, batches[0], out)
     return steps * sample / dt, dt / steps
 
 
@@ -188,8 +190,9 @@ def measure_dgemm_tflops(torch, n=8192, reps=5):
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from barefoot_framework_b200 import _lib, engine
+    from barefoot_framework_b200 import _lib, engine, util
     from barefoot_framework_b200 import dist as bdist
+    from barefoot_framework_b200.gpModel import gp_model
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -206,7 +209,6 @@ def run_gpu(args):
     Xd, yd = engine.to_dev(X), engine.to_dev(y)
     dev_batches = [engine.to_dev(b) for b in batches]
     host_batches = [torch.from_numpy(b).pin_memory() for b in batches]
-    host_X, host_y = torch.from_numpy(X).pin_memory(), torch.from_numpy(y).pin_memory()
     h2d_bytes = batches[0].nbytes + X.nbytes + y.nbytes
 
     def step(Xs_dev, Xt, yt):
@@ -218,10 +220,16 @@ def run_gpu(args):
         return bdist.reduce_candidate_shards(res.best_val[0, :3].contiguous(), res.best_idx[0, :3].contiguous(),
                                              rank * N_CAND)
 
+    # end to end through the reference-facing call: the truth GP object of the batch-only path
+    # (barefoot.py:771-773) and one util call per work item with HOST candidates (pinned memory)
+    model_gp = gp_model(X, y, np.ones(N_DIM), 1, sn, N_DIM, KERNEL)
+
     def step_e2e(b):
-        Xs_dev = host_batches[b].to(dev, non_blocking=True)
-        Xt, yt = host_X.to(dev, non_blocking=True), host_y.to(dev, non_blocking=True)
-        v, i = step(Xs_dev, Xt, yt)
+        out = util.batch_acquisition_multi(model_gp, hp, host_batches[b], curr_max, ("EI", "PI", "UCB"), ITERATION,
+                                           XI, return_device=True)
+        vals = torch.stack([out[nm][0][0] for nm in ("EI", "PI", "UCB")])
+        idxs = torch.stack([out[nm][1][0] for nm in ("EI", "PI", "UCB")])
+        v, i = bdist.reduce_candidate_shards(vals, idxs, rank * N_CAND)
         return v.cpu(), i.cpu()
 
     def barrier():
@@ -292,7 +300,16 @@ def run_gpu(args):
         if os.path.isfile(peaks):
             roofline["hbm_gbs_measured"] = json.load(open(peaks)).get("hbm_gbs")
         cpu_steps = 2
-        cpu_val = cpu_throughput(cpu_steps, 1)[0] if world == 1 else None      # N = 1 only (contract)
+        cpu_val, parity = None, None
+        if world == 1:                                                       # N = 1 only (contract)
+            cpu_val, _, (cX, cy, chp, csn, ccm, cXs, cout) = cpu_throughput(cpu_steps, 1, want_result=True)
+            # the same sample through the CUDA path: selections must be the oracle's
+            gout = util.batch_acquisition_multi(gp_model(cX, cy, np.ones(N_DIM), 1, csn, N_DIM, KERNEL), chp, cXs, ccm,
+                                                ("EI", "PI", "UCB"), ITERATION, XI)
+            parity = {"sample": CPU_SAMPLE,
+                      "indices_match": all(int(gout[nm][1][0]) == int(cout[k][1]) for k, nm in enumerate(("EI", "PI", "UCB"))),
+                      "max_rel_value_diff": max(abs(float(gout[nm][0][0]) - float(cout[k][0])) / max(1.0, abs(float(cout[k][0])))
+                                                for k, nm in enumerate(("EI", "PI", "UCB")))}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
                 "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(world),
@@ -301,7 +318,9 @@ def run_gpu(args):
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / steps},
                 "roofline": roofline,
                 "cpu_baseline": cpu_baseline_dict(cpu_val, CPU_SAMPLE, cpu_steps) if world == 1 else None,
-                "selected": {"EI": int(out[1][0]), "PI": int(out[1][1]), "UCB": int(out[1][2])}}
+                "selected": {"EI": int(out[1][0]), "PI": int(out[1][1]), "UCB": int(out[1][2])},
+                "selected_e2e": {"EI": int(out_e2e[1][0]), "PI": int(out_e2e[1][1]), "UCB": int(out_e2e[1][2])},
+                "parity_vs_cpu_oracle": parity}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
