@@ -6,4 +6,4 @@ acquisitionFunc, util, barefoot); every numeric call goes through the C ABI in
 include/barefoot_sm100.h (hand-written CUDA, no CPU fallback)."""
 from . import _lib  # noqa: F401
 
-__all__ = ["_lib", "engine", "gpModel", "reificationFusion", "acquisitionFunc", "util", "barefoot"]
+__all__ = ["_lib", "engine", "dist", "gpModel", "reificationFusion", "acquisitionFunc", "util", "barefoot", "subProcess"]

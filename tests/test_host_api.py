@@ -235,3 +235,40 @@ def test_batch_only_path_kg_uses_full_covariance(pkg):
         vals, idxs = pkg.util.batch_acquisition_batch(gp, g["hps"], g["x_test"], float(g["curr_max"]), "KG", iteration=2)
         np.testing.assert_array_equal(idxs, g[pre + "KG_idx"], err_msg=kern)
         np.testing.assert_allclose(vals, g[pre + "KG_val"], rtol=1e-7, atol=1e-10, err_msg=kern)
+
+
+def test_subprocess_worker_file_protocol(pkg, tmp_path):
+    """The multi-node worker serves the reference master's control/dump/output files."""
+    from barefoot_framework_b200 import subProcess
+    g = golden("workitems.npz")
+    pre = "c1_"
+    kern = str(g[pre + "kern"])
+    x_fused, x_test, hps = g[pre + "x_fused"], g[pre + "x_test"], g[pre + "hps"]
+    model = _model(pkg, g, pre)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        os.makedirs("data/parameterSets")
+        os.makedirs("subprocess")
+        with open("data/reificationObj", "wb") as f:
+            pickle.dump(model, f)
+        H = hps.shape[0]
+        data = [(3, [], x_fused, hps[mm], kern, x_test, float(g[pre + "curr_max"]), 0.01, "EI") for mm in range(H)]
+        with open("data/parameterSets/parameterSet0", "wb") as f:
+            pickle.dump(data, f)
+        with open("subprocess/0.dump", "wb") as f:
+            pickle.dump([[mm, 0] for mm in range(H)], f)
+        with open("subprocess/sub0.control", "wb") as f:
+            pickle.dump([0, "fused", "EI"], f)
+        assert subProcess.serve_once(0) is True
+        assert subProcess.serve_once(0) is False                     # flag flipped to "done"
+        with open("subprocess/sub0.control", "rb") as f:
+            assert pickle.load(f)[0] == 1
+        with open("subprocess/0.output", "rb") as f:
+            out = pickle.load(f)
+        from oracle import fast
+        ref = fast.dedupe_fused_output(g[pre + "tm_EI_val"], g[pre + "tm_EI_idx"], x_test.shape[0])
+        np.testing.assert_array_equal(out[:, 1], ref[:, 1])
+        np.testing.assert_allclose(out[:, 0], ref[:, 0], rtol=1e-8, atol=1e-11)
+    finally:
+        os.chdir(cwd)
