@@ -17,6 +17,17 @@ def world():
     return 0, 1
 
 
+def gather_host_sets(values, indices):
+    """gather_sets for host arrays (numpy in, numpy out); identity in a single process."""
+    r, w = world()
+    if w == 1:
+        return values, indices
+    import numpy as np
+    v, i = gather_sets(torch.as_tensor(np.ascontiguousarray(values, dtype=np.float64)),
+                       torch.as_tensor(np.ascontiguousarray(indices, dtype=np.int64)))
+    return v.cpu().numpy(), i.cpu().numpy()
+
+
 def shard_range(n, rank=None, world_size=None):
     """Contiguous, balanced split of n units: returns (start, stop) of this rank
     (the first n % world ranks get one extra unit)."""
@@ -28,12 +39,21 @@ def shard_range(n, rank=None, world_size=None):
     return start, start + base + (1 if rank < extra else 0)
 
 
+def _comm(t):
+    """gloo (CPU tests, or ranks sharing one GPU) exchanges host tensors; NCCL device tensors."""
+    if dist.get_backend() == "gloo" and t.is_cuda:
+        return t.cpu()
+    return t
+
+
 def gather_sets(values, indices):
     """Set-sharded stages: every rank holds (values [h_r], indices [h_r]) for its contiguous block of
     hyper-parameter sets; returns the concatenation over ranks in set order on every rank."""
     r, w = world()
     if w == 1:
         return values, indices
+    dev = values.device
+    values, indices = _comm(values), _comm(indices)
     n_local = torch.tensor([values.numel()], dtype=torch.int64, device=values.device)
     sizes = [torch.zeros_like(n_local) for _ in range(w)]
     dist.all_gather(sizes, n_local)
@@ -47,7 +67,7 @@ def gather_sets(values, indices):
     gi = [torch.empty_like(pi) for _ in range(w)]
     dist.all_gather(gv, pv)
     dist.all_gather(gi, pi)
-    return (torch.cat([g[:s] for g, s in zip(gv, sizes)]), torch.cat([g[:s] for g, s in zip(gi, sizes)]))
+    return (torch.cat([g[:s] for g, s in zip(gv, sizes)]).to(dev), torch.cat([g[:s] for g, s in zip(gi, sizes)]).to(dev))
 
 
 def reduce_candidate_shards(values, indices, index_offset):
@@ -59,6 +79,8 @@ def reduce_candidate_shards(values, indices, index_offset):
     gidx = indices + int(index_offset)
     if w == 1:
         return values, gidx
+    dev = values.device
+    values, gidx = _comm(values), _comm(gidx)
     gv = [torch.empty_like(values) for _ in range(w)]
     gi = [torch.empty_like(gidx) for _ in range(w)]
     dist.all_gather(gv, values)
@@ -66,7 +88,7 @@ def reduce_candidate_shards(values, indices, index_offset):
     gv, gi = torch.stack(gv), torch.stack(gi)            # [world, S]
     best = gv.max(dim=0).values
     cand = torch.where(gv == best, gi, torch.full_like(gi, _BIG))
-    return best, cand.min(dim=0).values
+    return best.to(dev), cand.min(dim=0).values.to(dev)
 
 
 def reduce_top2(t1, i1, t2, index_offset):
@@ -76,6 +98,8 @@ def reduce_top2(t1, i1, t2, index_offset):
     gi1 = i1 + int(index_offset)
     if w == 1:
         return t1, gi1, t2
+    dev = t1.device
+    t1, gi1, t2 = _comm(t1), _comm(gi1), _comm(t2)
     a = [torch.empty_like(t1) for _ in range(w)]
     b = [torch.empty_like(gi1) for _ in range(w)]
     c = [torch.empty_like(t2) for _ in range(w)]
@@ -90,4 +114,4 @@ def reduce_top2(t1, i1, t2, index_offset):
     winner = is_best & (b == first)
     others = torch.where(winner, torch.full_like(a, float("-inf")), a)
     second = torch.maximum(others.max(dim=0).values, c.max(dim=0).values)
-    return best, first, second
+    return best.to(dev), first.to(dev), second.to(dev)

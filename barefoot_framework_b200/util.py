@@ -12,6 +12,7 @@ from pickle import dump, load
 import numpy as np
 import torch
 
+from . import dist as bdist
 from . import engine
 from .acquisitionFunc import thompson_sampling
 from .engine import ACQ_BITS, ACQ_EI, ACQ_GREEDY, ACQ_PI, ACQ_UCB, SLOT_EI, SLOT_GREEDY, SLOT_PI, SLOT_UCB
@@ -108,12 +109,18 @@ def fused_calculate_batch(model, x_fused, hp_sets, kernel, x_test, curr_max, sam
     """Every work item of barefoot.py:1222-1283 in one device pass.  Returns (values [H],
     indices [H]); for sampleOpt "Hedge" a list of H lists of six [value, index] pairs."""
     x_test = np.asarray(x_test, dtype=np.float64)
-    f, scale, shift = model.create_fused_GP_batch(x_fused, hp_sets, kernel, targets=targets)
+    hp = np.atleast_2d(np.asarray(hp_sets, dtype=np.float64))
+    deterministic = sampleOpt not in ("Hedge", "TS")          # host RNG draws must stay in one stream
+    lo, hi = bdist.shard_range(hp.shape[0]) if deterministic else (0, hp.shape[0])
+    f, scale, shift = model.create_fused_GP_batch(x_fused, hp[lo:hi], kernel, targets=targets)
     if sampleOpt == "Hedge":
         r = _sweep(f, scale, shift, x_test, _HEDGE_ORDER, "TM", curr_max, iteration, xi)
         return [[[r[nm][0][h], int(r[nm][1][h])] for nm in _HEDGE_ORDER] for h in range(f.S)]
     name = sampleOpt if sampleOpt in ("KG", "TS", "EI", "PI", "UCB") else "Greedy"
     r = _sweep(f, scale, shift, x_test, [name], "TM", curr_max, iteration, xi)
+    if deterministic:
+        # hyper-parameter sets are sharded over the ranks of a torchrun job; only (value, index) travels
+        return bdist.gather_host_sets(*r[name])
     return r[name]
 
 
@@ -272,6 +279,9 @@ def batch_acquisition_batch(modelGP, hp_sets, x_test, curr_max, acqFunc, iterati
     posterior covariance (util.py:1078-1081) and runs per set through bf_kg_full."""
     x_test = np.asarray(x_test, dtype=np.float64)
     hp = np.atleast_2d(np.asarray(hp_sets, dtype=np.float64))
+    if acqFunc not in ("KG", "Hedge", "TS"):
+        lo, hi = bdist.shard_range(hp.shape[0])           # sets sharded over ranks, gathered below
+        hp = hp[lo:hi]
     x = np.asarray(modelGP.x_train, dtype=np.float64)
     x = x.reshape(x.shape[0], -1)
     y = np.asarray(modelGP.y_train, dtype=np.float64) - float(modelGP.mean)
@@ -291,6 +301,8 @@ def batch_acquisition_batch(modelGP, hp_sets, x_test, curr_max, acqFunc, iterati
         return [[[r[nm][0][h], int(r[nm][1][h])] for nm in _HEDGE_ORDER] for h in range(f.S)]
     name = acqFunc if acqFunc in ("TS", "EI", "PI", "UCB") else "Greedy"
     r = _sweep(f, scale, shift, x_test, [name], "BATCH", curr_max, iteration, xi)
+    if name != "TS":
+        return bdist.gather_host_sets(*r[name])
     return r[name]
 
 

@@ -89,3 +89,37 @@ def test_single_process_is_identity():
     assert bd.shard_range(10) == (0, 10)
     gv, gi = bd.reduce_candidate_shards(v, i, 5)
     assert torch.equal(gv, v) and torch.equal(gi, i + 5)
+
+
+def _tm_stage_sharded(rank, world):
+    """Two ranks (gloo; both on cuda:0) shard the hyper-parameter sets of a TM-stage call."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    from conftest import golden
+    import barefoot_framework_b200 as pkg
+    from barefoot_framework_b200 import reificationFusion, util
+    g = golden("workitems.npz")
+    pre = "c1_"
+    model = reificationFusion.model_reification(
+        [g[pre + f"x_train{i}"].copy() for i in range(3)], [g[pre + f"y_train{i}"].copy() for i in range(3)],
+        g[pre + "model_l"], g[pre + "model_sf"], g[pre + "model_sn"], g[pre + "means"], g[pre + "std"],
+        g[pre + "err_l"], g[pre + "err_sf"], g[pre + "err_sn"], g[pre + "x_true"].copy(), g[pre + "y_true"].copy(),
+        3, int(g[pre + "d"]), str(g[pre + "kern"]))
+    out = {}
+    for opt in ("KG", "EI", "Greedy"):
+        v, i = util.fused_calculate_batch(model, g[pre + "x_fused"], g[pre + "hps"], str(g[pre + "kern"]),
+                                          g[pre + "x_test"], float(g[pre + "curr_max"]), opt, iteration=3)
+        out[opt] = (np.asarray(v), np.asarray(i), g[pre + f"tm_{opt}_val"], g[pre + f"tm_{opt}_idx"])
+    return out
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_tm_stage_sharded_over_two_ranks_matches_reference():
+    res = _run(_tm_stage_sharded)
+    for out in res:
+        for opt, (v, i, rv, ri) in out.items():
+            np.testing.assert_array_equal(i, ri, err_msg=opt)
+            np.testing.assert_allclose(v, rv, rtol=1e-8, atol=1e-11, err_msg=opt)
