@@ -38,13 +38,14 @@ struct PostParams {
 
 // ---- phase A ------------------------------------------------------------------------------
 // B-tile layout: cell ((g * NTA + a) * 32 + lane) holds k*[4g + (lane & 3)][8a + (lane >> 2)], the
-// DMMA B fragment of atom a at k-group g.  Warp w generates k-groups g = w, w+8, ...
+// DMMA B fragment of atom a at k-group g.  The calling warp generates k-groups g_first, g_first +
+// g_stride, ... < g_end and leaves its share of the mean in row `slot` of mpart.
 template <int D, int NTA>
 __device__ __forceinline__ void gen_tile(const PostParams& p, const double* __restrict__ w_s,
                                          const double* __restrict__ xs_s, double* __restrict__ Bt,
                                          double* __restrict__ mpart, const double* __restrict__ alpha,
-                                         double amp, const double* __restrict__ tab, int warp,
-                                         int nwarps = BF_WARPS) {
+                                         double amp, const double* __restrict__ tab, int g_first, int g_stride,
+                                         int g_end, int slot) {
     constexpr int NT = 8 * NTA;
     constexpr int DR = D ? D : BF_MAX_DIM;   // D == 0: nDim is a run-time value (9..16)
     const int dd = D ? D : p.d;
@@ -53,53 +54,33 @@ __device__ __forceinline__ void gen_tile(const PostParams& p, const double* __re
     double w[DR];
 #pragma unroll
     for (int a = 0; a < DR; ++a) w[a] = a < dd ? w_s[a] : 0.0;           // metric scale (bf_metric_scale)
-    const double* xc = xs_s + nn;            // this lane's candidates: xc[a * NT + 8 * at]
+    const double* xc = xs_s + nn;            // this lane's candidates (pre-scaled): xc[a * NT + 8 * at]
     double macc[NTA];
 #pragma unroll
     for (int at = 0; at < NTA; ++at) macc[at] = 0.0;
 
-    // G k-groups per trip: G * NTA independent (branch-free) evaluation chains per lane hide the
-    // latency of the FP64 pipe, which these warps share with the DMMA warps
-    constexpr int G = 1;
-    const int ng = p.np >> 2;
-    for (int g0 = warp; g0 < ng; g0 += G * nwarps) {
-        double xj[G][DR], aj[G];
+    // NTA independent branch-free evaluation chains per lane; the FP64 FMA pipe is the limit here
+    for (int g = g_first; g < g_end; g += g_stride) {
+        const int j = 4 * g + kk;
+        const bool valid = j < p.n;
+        double xj[DR];
 #pragma unroll
-        for (int h = 0; h < G; ++h) {
-            const int j = 4 * (g0 + h * nwarps) + kk;
-            const bool valid = (g0 + h * nwarps) < ng && j < p.n;
+        for (int a = 0; a < DR; ++a) xj[a] = (valid && a < dd) ? __ldg(p.X + (size_t)j * dd + a) * w[a] : 0.0;
+        const double aj = valid ? __ldg(alpha + j) : 0.0;
+        double* out = Bt + (size_t)g * NTA * 32 + lane;
 #pragma unroll
-            for (int a = 0; a < DR; ++a) xj[h][a] = (valid && a < dd) ? __ldg(p.X + (size_t)j * dd + a) * w[a] : 0.0;
-            aj[h] = valid ? __ldg(alpha + j) : 0.0;
-        }
-        double v[G][NTA];
+        for (int at = 0; at < NTA; ++at) {
+            double q = 0.0;
 #pragma unroll
-        for (int h = 0; h < G; ++h)
-#pragma unroll
-            for (int at = 0; at < NTA; ++at) {
-                double q = 0.0;
-#pragma unroll
-                for (int a = 0; a < DR; ++a) {
-                    if (a < dd) {
-                        const double df = xc[a * NT + 8 * at] - xj[h][a];      // both pre-scaled
-                        q = fma(df, df, q);
-                    }
-                }
-                v[h][at] = amp * bf_radial_q(p.kern, q, tab);
-            }
-#pragma unroll
-        for (int h = 0; h < G; ++h) {
-            const int g = g0 + h * nwarps;
-            if (g < ng) {
-                const bool valid = 4 * g + kk < p.n;
-                double* out = Bt + (size_t)g * NTA * 32 + lane;
-#pragma unroll
-                for (int at = 0; at < NTA; ++at) {
-                    const double val = valid ? v[h][at] : 0.0;
-                    macc[at] = fma(aj[h], val, macc[at]);
-                    out[at * 32] = val;
+            for (int a = 0; a < DR; ++a) {
+                if (a < dd) {
+                    const double df = xc[a * NT + 8 * at] - xj[a];              // both pre-scaled
+                    q = fma(df, df, q);
                 }
             }
+            const double val = valid ? amp * bf_radial_q(p.kern, q, tab) : 0.0;
+            macc[at] = fma(aj, val, macc[at]);
+            out[at * 32] = val;
         }
     }
     // mean partials: sum over the 4 kk lanes, then one slot per warp (fixed-order sum later)
@@ -108,7 +89,7 @@ __device__ __forceinline__ void gen_tile(const PostParams& p, const double* __re
         double v = macc[at];
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
-        if (kk == 0) mpart[warp * NT + 8 * at + nn] = v;
+        if (kk == 0) mpart[slot * NT + 8 * at + nn] = v;
     }
 }
 
@@ -262,7 +243,8 @@ __global__ void __launch_bounds__(BF_THREADS, MINB) bf_posterior_kernel(PostPara
     }
     __syncthreads();
 
-    gen_tile<D, NTA>(p, w_s, xs_s, Bt, mpart, p.alpha + (size_t)set * p.n, amp, tab_s, threadIdx.x >> 5);
+    gen_tile<D, NTA>(p, w_s, xs_s, Bt, mpart, p.alpha + (size_t)set * p.n, amp, tab_s, threadIdx.x >> 5, BF_WARPS,
+                     p.np >> 2, threadIdx.x >> 5);
     __syncthreads();
 
     const double* Aset = p.linv + (size_t)set * p.linv_stride;
@@ -387,9 +369,9 @@ __global__ void __launch_bounds__(BF_DUAL_THREADS, 1) bf_posterior_dual_kernel(P
     const int grp = warp >> 3, gw = warp & 7, gtid = threadIdx.x & (BF_THREADS - 1);
     double* Bt = smem + grp * bt_sz;                                    // 2 x np * NT
     double* xs_s = smem + 2 * bt_sz + grp * dd * NT;                    // 2 x d * NT
-    double* mpart = smem + 2 * bt_sz + 2 * dd * NT + grp * BF_WARPS * NT;          // 2 x BF_WARPS * NT
-    double* spart = smem + 2 * bt_sz + 2 * dd * NT + (2 + grp) * BF_WARPS * NT;    // 2 x BF_WARPS * NT
-    double* w_s = smem + 2 * bt_sz + 2 * dd * NT + 4 * BF_WARPS * NT;   // BF_MAX_DIM
+    double* mpart = smem + 2 * bt_sz + 2 * dd * NT + grp * BF_WARPS * NT;          // 2 buffers x 2 groups x BF_WARPS * NT
+    double* spart = smem + 2 * bt_sz + 2 * dd * NT + (4 + grp) * BF_WARPS * NT;    // 2 groups x BF_WARPS * NT
+    double* w_s = smem + 2 * bt_sz + 2 * dd * NT + 6 * BF_WARPS * NT;   // BF_MAX_DIM
     double* tab_s = w_s + BF_MAX_DIM;                                   // BF_EXP_TAB_N
 
     const int set = blockIdx.y;
@@ -413,49 +395,94 @@ __global__ void __launch_bounds__(BF_DUAL_THREADS, 1) bf_posterior_dual_kernel(P
     for (int k = 0; k < 3; ++k) best[k] = bf_best_init();
     BfTop2 top = bf_top2_init();
 
-    for (long long tp = t0; tp < t1; tp += 2) {
-        const long long tile = tp + grp;
-        const bool active = tile < t1;
-        const long long c_base = tile * NT;
-        for (int e = gtid; e < dd * NT; e += BF_THREADS) {
-            const int a = e / NT, c = e - a * NT;
-            const long long gi = c_base + c;
-            xs_s[e] = (active && gi < p.N) ? p.Xs[gi * dd + a] * w_s[a] : 0.0;      // pre-scaled by the metric
+    // k-groups of phase A per warp: contiguous ranges; warp 0 of each group also finishes the previous
+    // tile (phase C) while the others generate, so it takes a smaller share
+    const int ng = p.np >> 2;
+    int g_lo, g_hi;
+    {
+        const int per = ng / BF_WARPS;
+        int w0 = per - (per >= 6 ? (per + 5) / 8 : 0);
+        if (w0 < 1) w0 = per;
+        const int rest = ng - w0;                                  // shared by warps 1..7
+        if (gw == 0) {
+            g_lo = 0;
+            g_hi = w0;
+        } else {
+            g_lo = w0 + (int)((long long)rest * (gw - 1) / (BF_WARPS - 1));
+            g_hi = w0 + (int)((long long)rest * gw / (BF_WARPS - 1));
         }
-        __syncthreads();     // also orders the previous phase C before mpart / spart are rewritten
-        if (active && !(p.debug_skip & 2)) gen_tile<D, NTA>(p, w_s, xs_s, Bt, mpart, alpha, amp, tab_s, gw);
-        __syncthreads();
-        if (active && !(p.debug_skip & 1)) dual_mma<NTA>(p.nb, Aset, Bt, spart, gw);
-        __syncthreads();
-        if (active && gw == 0 && !(p.debug_skip & 4)) {
-            // ---- phase C: one lane per candidate (two rounds when the tile has 48) ----
+    }
+
+    // phase C of one tile: one lane per candidate (two rounds when the tile has 48)
+    auto finish_tile = [&](long long tile, const double* mp) {
+        const long long cb = tile * NT;
 #pragma unroll
-            for (int c = lane; c < NT; c += 32) {
-                const long long gi = c_base + c;
-                if (gi < p.N) {
-                    double mean = 0.0, s = 0.0;
+        for (int c = lane; c < NT; c += 32) {
+            const long long gi = cb + c;
+            if (gi < p.N) {
+                double mean = 0.0, s = 0.0;
 #pragma unroll
-                    for (int w = 0; w < BF_WARPS; ++w) mean += mpart[w * NT + c];
+                for (int w = 0; w < BF_WARPS; ++w) mean += mp[w * NT + c];
 #pragma unroll
-                    for (int w = 0; w < BF_WARPS; ++w) s += spart[w * NT + c];
-                    const double mu = mean * sc + sh;
-                    const double var = (amp - s) * (sc * sc);
-                    if (p.mu_out) p.mu_out[(size_t)set * p.N + gi] = mu;
-                    if (p.var_out) p.var_out[(size_t)set * p.N + gi] = var;
-                    if (p.acq_mask) {
-                        const double spread = p.spread_is_sqrt ? sqrt(var) : var;
-                        if (p.acq_mask & BF_ACQ_EI)
-                            bf_best_take(best[BF_SLOT_EI],
-                                         (mu - p.curr_max - p.xi) * bf_norm_pdf(mu) + var * bf_norm_cdf(mu), gi);
-                        if (p.acq_mask & BF_ACQ_PI)
-                            bf_best_take(best[BF_SLOT_PI], bf_norm_cdf((mu - p.curr_max - p.xi) / spread), gi);
-                        if (p.acq_mask & BF_ACQ_UCB) bf_best_take(best[BF_SLOT_UCB], mu + p.kt * spread, gi);
-                        if (p.acq_mask & BF_ACQ_GREEDY) bf_top2_merge(top, mu, gi, -INFINITY);
-                    }
+                for (int w = 0; w < BF_WARPS; ++w) s += spart[w * NT + c];
+                const double mu = mean * sc + sh;
+                const double var = (amp - s) * (sc * sc);
+                if (p.mu_out) p.mu_out[(size_t)set * p.N + gi] = mu;
+                if (p.var_out) p.var_out[(size_t)set * p.N + gi] = var;
+                if (p.acq_mask) {
+                    const double spread = p.spread_is_sqrt ? sqrt(var) : var;
+                    if (p.acq_mask & BF_ACQ_EI)
+                        bf_best_take(best[BF_SLOT_EI],
+                                     (mu - p.curr_max - p.xi) * bf_norm_pdf(mu) + var * bf_norm_cdf(mu), gi);
+                    if (p.acq_mask & BF_ACQ_PI)
+                        bf_best_take(best[BF_SLOT_PI], bf_norm_cdf((mu - p.curr_max - p.xi) / spread), gi);
+                    if (p.acq_mask & BF_ACQ_UCB) bf_best_take(best[BF_SLOT_UCB], mu + p.kt * spread, gi);
+                    if (p.acq_mask & BF_ACQ_GREEDY) bf_top2_merge(top, mu, gi, -INFINITY);
                 }
             }
         }
+    };
+
+    // candidate coordinates of a tile: global -> registers (issued before phase B) -> shared memory
+    constexpr int XR = (BF_MAX_DIM * NT + BF_THREADS - 1) / BF_THREADS;
+    double xr[XR];
+    auto fetch_xs = [&](long long tile) {
+        const long long cb = tile * NT;
+#pragma unroll
+        for (int k = 0; k < XR; ++k) {
+            const int e = gtid + k * BF_THREADS;
+            const int a = e / NT, c = e - a * NT;
+            const long long gi = cb + c;
+            xr[k] = (e < dd * NT && tile < t1 && gi < p.N) ? p.Xs[gi * dd + a] * w_s[a] : 0.0;   // pre-scaled
+        }
+    };
+    auto store_xs = [&]() {
+#pragma unroll
+        for (int k = 0; k < XR; ++k) {
+            const int e = gtid + k * BF_THREADS;
+            if (e < dd * NT) xs_s[e] = xr[k];
+        }
+    };
+
+    fetch_xs(t0 + grp);
+    store_xs();
+    long long prev_tile = -1;
+    int buf = 0;
+    for (long long tp = t0; tp < t1; tp += 2, buf ^= 1) {
+        const long long tile = tp + grp;
+        const bool active = tile < t1;
+        double* mp_cur = mpart + buf * 2 * BF_WARPS * NT;
+        __syncthreads();     // candidates staged; phase B of the previous pair complete (column sums ready)
+        if (gw == 0 && prev_tile >= 0 && !(p.debug_skip & 4)) finish_tile(prev_tile, mpart + (buf ^ 1) * 2 * BF_WARPS * NT);
+        if (active && !(p.debug_skip & 2)) gen_tile<D, NTA>(p, w_s, xs_s, Bt, mp_cur, alpha, amp, tab_s, g_lo, 1, g_hi, gw);
+        __syncthreads();
+        fetch_xs(tile + 2);                                  // in flight during phase B
+        if (active && !(p.debug_skip & 1)) dual_mma<NTA>(p.nb, Aset, Bt, spart, gw);
+        store_xs();
+        prev_tile = active ? tile : -1;
     }
+    __syncthreads();
+    if (gw == 0 && prev_tile >= 0 && !(p.debug_skip & 4)) finish_tile(prev_tile, mpart + (buf ^ 1) * 2 * BF_WARPS * NT);
     if (!p.acq_mask) return;
     // the two finishing warps (warp 0 of each group) merge through shared memory
     __shared__ BfBest red_best[3][2];
@@ -561,7 +588,7 @@ extern "C" size_t bf_linv_packed_doubles(int n) {
 // whenever it fits; otherwise the single-buffer kernel with one CTA per SM.
 struct TileChoice { int NT; int dual; };
 static size_t posterior_dual_smem_bytes(int np, int NT, int d) {
-    return sizeof(double) * (2 * ((size_t)np * NT + (size_t)d * NT) + 4 * (size_t)BF_WARPS * NT + BF_MAX_DIM + BF_EXP_TAB_N);
+    return sizeof(double) * (2 * ((size_t)np * NT + (size_t)d * NT) + 6 * (size_t)BF_WARPS * NT + BF_MAX_DIM + BF_EXP_TAB_N);
 }
 static TileChoice choose_tile(int n) {
     const int np = bf_padded_n(n);

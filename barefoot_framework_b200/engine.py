@@ -25,6 +25,28 @@ def device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_copy_stream = None
+
+
+def to_dev_async(a, dtype=F64):
+    """Host -> device copy of a (pinned) host tensor / array on a side stream, so it overlaps the GP
+    set-up kernels of the same work item.  Returns (device tensor, event to wait on); tensors that
+    already live on the device come back with event None."""
+    global _copy_stream
+    if isinstance(a, torch.Tensor) and a.is_cuda:
+        return a.to(dtype=dtype).contiguous(), None
+    dev = device()
+    t = a if isinstance(a, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(a))
+    t = t.to(dtype=dtype).contiguous()
+    if _copy_stream is None:
+        _copy_stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(_copy_stream):
+        out = t.to(dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(_copy_stream)
+    return out, ev
+
+
 def to_dev(a, dtype=F64):
     if isinstance(a, torch.Tensor):
         return a.to(device=device(), dtype=dtype).contiguous()

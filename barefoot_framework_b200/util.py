@@ -313,10 +313,15 @@ def batch_acquisition_multi(modelGP, hp_sets, x_test, curr_max, names=("EI", "PI
     device tensor), then every requested acquisition fused into the epilogue.  Returns
     {name: (values [H], indices [H])} as host arrays, or device tensors with return_device."""
     hp = np.atleast_2d(np.asarray(hp_sets, dtype=np.float64))
+    # the candidates travel host -> device on a side stream while the GPs are factorised
+    x_test, copied = engine.to_dev_async(x_test)
     x = np.asarray(modelGP.x_train, dtype=np.float64)
     x = x.reshape(x.shape[0], -1)
     y = np.asarray(modelGP.y_train, dtype=np.float64) - float(modelGP.mean)
     f = engine.build_factors(modelGP.kern, x, y, hp[:, 1:], hp[:, 0], modelGP.sigma_n, ndim=modelGP.n_dim)
+    if copied is not None:
+        torch.cuda.current_stream().wait_event(copied)
+        x_test.record_stream(torch.cuda.current_stream())
     mask = 0
     for nm in names:
         mask |= ACQ_BITS[nm]
