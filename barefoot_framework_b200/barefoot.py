@@ -480,9 +480,14 @@ class barefoot():
                 prob = self.gpHedgeProb / np.sum(self.gpHedgeProb)
                 chosen = np.where(prob == np.max(prob))[0][0]
                 self.gpHedgeTrack.append(chosen)
-                self._hedge_clusters = [x_test[self._cluster_rom(np.array(out[k], dtype=object))[:, 2].astype(int), :]
+                # The reference's pool returns one entry per WORK ITEM (each holding the six portfolio
+                # rows) and then indexes that list with the portfolio index (barefoot.py:1509-1521): the
+                # rows of work item `chosen` are clustered, and work items 0..5 feed the gain update.
+                # Reproduced as is.
+                items = [[out[k][s_] for k in range(6)] for s_ in range(len(out[0]))]
+                self._hedge_clusters = [x_test[self._cluster_rom(np.array(items[k]))[:, 2].astype(int), :]
                                         for k in range(6)]
-                kg_output = np.array(out[chosen], dtype=object)
+                kg_output = np.array(items[chosen], dtype=object)
             else:
                 kg_output = np.array(out, dtype=object)
             medoid_out = self._cluster_rom(kg_output)

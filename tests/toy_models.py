@@ -69,6 +69,9 @@ CASES = [
                                    initDataPathorNum=[3, 2, 3, 2]),
      dict(covFunc="M32", iterLimit=2, sampleCount=8, hpCount=10, batchSize=2, tmIter=1, fusedPoints=10,
           fusedSamples=80), 2),
+    ("reifi_hedge", dict(reification=True, acquisitionFunc="Hedge", tmSampleOpt="Hedge", initDataPathorNum=[3, 3, 3, 3]),
+     dict(covFunc="M52", iterLimit=2, sampleCount=6, hpCount=8, batchSize=2, tmIter=1, fusedPoints=10,
+          fusedSamples=60, lowBound=0.05), 4),
     ("batch_only_ei", dict(reification=False, acquisitionFunc="EI", tmSampleOpt="EI", initDataPathorNum=[4]),
      dict(covFunc="M32", iterLimit=3, sampleCount=30, hpCount=25, batchSize=3, tmIter=5, fusedPoints=10,
           fusedHP=[3, 0.1, 0.1]), 3),
