@@ -47,6 +47,9 @@ SIGNATURES = {
     "bf_kmedoids_rowsum": (c_i, [c_ll, c_i, c_p, c_ll, c_ll, c_p, c_p]),
     "bf_kmedoids_assign": (c_i, [c_ll, c_i, c_i, c_p, c_p, c_p, c_p]),
     "bf_kmedoids_cluster_cost": (c_i, [c_ll, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "bf_kmedoids_cluster_cost_part": (c_i, [c_ll, c_i, c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_p]),
+    "bf_kmedoids_sort_workspace": (c_sz, [c_ll, c_i]),
+    "bf_kmedoids_sort_labels": (c_i, [c_ll, c_i, c_p, c_p, c_p, c_p, c_p]),
     "bf_kmedoids_update": (c_i, [c_ll, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     "bf_affine": (c_i, [c_ll, c_p, c_d, c_d, c_p, c_p]),
     "bf_total_variance": (c_i, [c_ll, c_p, c_d, c_d, c_p, c_d, c_p, c_p]),

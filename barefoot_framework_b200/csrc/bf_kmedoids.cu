@@ -118,41 +118,190 @@ extern "C" int bf_kmedoids_assign(long long N, int f, int k, const double* X, co
     return 0;
 }
 
-// cost[p] = sum over the segment of p of |x_perm[p] - x_perm[q]|, q in segment order
-__global__ void __launch_bounds__(KM_THREADS) bf_km_cost_kernel(long long N, int f, int k,
-                                                                const double* __restrict__ X,
+// ---- stable counting sort of the labels: perm = rows ordered by (label, row), seg = cluster offsets ----
+// np.where(labels == c)[0] for every c in one pass (the member order defines cost ties and the
+// "first argmin").  Three small launches: per-block histograms, one scan over (cluster, block),
+// and a scatter in which every row counts the equal labels before it inside its block.
+#define KM_SORT_BLOCK 1024
+
+__global__ void __launch_bounds__(256) bf_km_hist_kernel(long long N, int k, const int32_t* __restrict__ labels,
+                                                         int nblk, long long* __restrict__ counts) {
+    extern __shared__ int hist[];          // k
+    for (int c = threadIdx.x; c < k; c += blockDim.x) hist[c] = 0;
+    __syncthreads();
+    const long long i0 = (long long)blockIdx.x * KM_SORT_BLOCK;
+    for (int t = threadIdx.x; t < KM_SORT_BLOCK; t += blockDim.x)
+        if (i0 + t < N) atomicAdd(&hist[labels[i0 + t]], 1);
+    __syncthreads();
+    for (int c = threadIdx.x; c < k; c += blockDim.x) counts[(size_t)c * nblk + blockIdx.x] = hist[c];
+}
+
+// exclusive scan over the cluster-major (cluster, block) counts; one CTA, chunked Hillis-Steele
+__global__ void __launch_bounds__(1024) bf_km_scan_kernel(int k, int nblk, long long* __restrict__ counts,
+                                                          long long* __restrict__ seg) {
+    __shared__ long long buf[1024];
+    __shared__ long long carry;
+    const long long total = (long long)k * nblk;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (long long e0 = 0; e0 < total; e0 += 1024) {
+        const long long e = e0 + threadIdx.x;
+        const long long v = e < total ? counts[e] : 0;
+        buf[threadIdx.x] = v;
+        __syncthreads();
+        for (int s = 1; s < 1024; s <<= 1) {
+            const long long add = threadIdx.x >= s ? buf[threadIdx.x - s] : 0;
+            __syncthreads();
+            buf[threadIdx.x] += add;
+            __syncthreads();
+        }
+        const long long excl = carry + buf[threadIdx.x] - v;
+        if (e < total) {
+            counts[e] = excl;
+            if (e % nblk == 0) seg[e / nblk] = excl;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += buf[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) seg[k] = carry;
+}
+
+__global__ void __launch_bounds__(256) bf_km_scatter_kernel(long long N, const int32_t* __restrict__ labels, int nblk,
+                                                            const long long* __restrict__ offsets,
+                                                            long long* __restrict__ perm) {
+    __shared__ int lab[KM_SORT_BLOCK];
+    const long long i0 = (long long)blockIdx.x * KM_SORT_BLOCK;
+    for (int t = threadIdx.x; t < KM_SORT_BLOCK; t += blockDim.x) lab[t] = (i0 + t < N) ? labels[i0 + t] : -1;
+    __syncthreads();
+    for (int t = threadIdx.x; t < KM_SORT_BLOCK; t += blockDim.x) {
+        if (i0 + t >= N) continue;
+        const int me = lab[t];
+        int before = 0;
+        for (int u = 0; u < t; ++u) before += (lab[u] == me);
+        perm[offsets[(size_t)me * nblk + blockIdx.x] + before] = i0 + t;
+    }
+}
+
+extern "C" size_t bf_kmedoids_sort_workspace(long long N, int k) {
+    const long long nblk = (N + KM_SORT_BLOCK - 1) / KM_SORT_BLOCK;
+    return sizeof(long long) * (size_t)(nblk > 0 ? nblk : 1) * (size_t)(k > 0 ? k : 1);
+}
+
+extern "C" int bf_kmedoids_sort_labels(long long N, int k, const int32_t* labels, long long* perm, long long* seg,
+                                       void* workspace, void* stream) {
+    BF_CHECK_ARG(N > 0 && k > 0 && labels && perm && seg && workspace, BF_ERR_ARG, "bf_kmedoids_sort_labels: bad argument");
+    BF_CHECK_ARG((size_t)k * sizeof(int) <= 48 * 1024, BF_ERR_SIZE, "bf_kmedoids_sort_labels: k too large");
+    const long long nblk = (N + KM_SORT_BLOCK - 1) / KM_SORT_BLOCK;
+    BF_CHECK_ARG(nblk <= 0x7fffffffLL, BF_ERR_SIZE, "bf_kmedoids_sort_labels: N too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    long long* counts = (long long*)workspace;
+    bf_km_hist_kernel<<<(unsigned)nblk, 256, (size_t)k * sizeof(int), st>>>(N, k, labels, (int)nblk, counts);
+    bf_km_scan_kernel<<<1, 1024, 0, st>>>(k, (int)nblk, counts, seg);
+    bf_km_scatter_kernel<<<(unsigned)nblk, 256, 0, st>>>(N, labels, (int)nblk, counts, perm);
+    BF_CHECK_LAUNCH("bf_kmedoids_sort_labels");
+    return 0;
+}
+
+// ---- in-cluster cost: cost[p] = sum over the segment of p of |x_perm[p] - x_perm[q]|, q in segment order ----
+// Work is cut into chunks of KM_THREADS consecutive positions of ONE cluster, numbered cluster-major;
+// chunk b is computed by the call with b % nparts == part (ranks of a multi-GPU job take one part
+// each; untouched positions keep the caller's zeros so the parts combine by addition).  The members of
+// the cluster are staged through shared memory tile by tile like the row-sum kernel; accumulation
+// order per position: four interleaved partial sums over q - q0 mod 4, remainder into the first.
+template <int F>
+__global__ void __launch_bounds__(KM_THREADS) bf_km_cost_kernel(int k, const double* __restrict__ X,
                                                                 const long long* __restrict__ perm,
-                                                                const long long* __restrict__ seg,
+                                                                const long long* __restrict__ seg, int part, int nparts,
                                                                 double* __restrict__ cost) {
-    const long long p = (long long)blockIdx.x * KM_THREADS + threadIdx.x;
-    if (p >= N) return;
-    int lo = 0, hi = k;           // segment c with seg[c] <= p < seg[c + 1]
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (seg[mid] <= p) lo = mid; else hi = mid;
+    constexpr int TILE = (F <= 4) ? KM_TILE : KM_TILE / 2;
+    __shared__ double tile[TILE * F];
+    __shared__ long long s_q0, s_q1, s_p0;
+    if (threadIdx.x == 0) {
+        // chunk index -> (cluster, first position): walk the clusters (k is small)
+        const long long b = (long long)blockIdx.x * nparts + part;
+        long long acc = 0;
+        s_q0 = s_q1 = s_p0 = -1;
+        for (int c = 0; c < k; ++c) {
+            const long long n_c = seg[c + 1] - seg[c];
+            const long long chunks = (n_c + KM_THREADS - 1) / KM_THREADS;
+            if (b < acc + chunks) {
+                s_q0 = seg[c];
+                s_q1 = seg[c + 1];
+                s_p0 = seg[c] + (b - acc) * KM_THREADS;
+                break;
+            }
+            acc += chunks;
+        }
     }
-    const long long q0 = seg[lo], q1 = seg[lo + 1];
-    double xi[KM_MAX_F];
-    const long long me = perm[p];
-    for (int a = 0; a < f; ++a) xi[a] = X[(size_t)me * f + a];
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    long long q = q0;
-    for (; q + 4 <= q1; q += 4) {
+    __syncthreads();
+    const long long q0 = s_q0, q1 = s_q1;
+    if (q0 < 0) return;                         // past the last chunk
+    const long long p = s_p0 + threadIdx.x;
+    const bool live = p < q1;
+    double xi[F];
+    {
+        const long long me = live ? perm[p] : 0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] += km_dist(xi, X + (size_t)perm[q + u] * f, f);
+        for (int c = 0; c < F; ++c) xi[c] = live ? X[(size_t)me * F + c] : 0.0;
     }
-    for (; q < q1; ++q) acc[0] += km_dist(xi, X + (size_t)perm[q] * f, f);
-    cost[p] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long j0 = q0; j0 < q1; j0 += TILE) {
+        const int cnt = (int)((q1 - j0 < TILE) ? (q1 - j0) : TILE);
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt; e += KM_THREADS) {
+            const long long row = perm[j0 + e];
+#pragma unroll
+            for (int c = 0; c < F; ++c) tile[e * F + c] = X[(size_t)row * F + c];
+        }
+        __syncthreads();
+        int j = 0;
+        for (; j + 4 <= cnt; j += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                double s = 0.0;
+#pragma unroll
+                for (int c = 0; c < F; ++c) {
+                    const double d = xi[c] - tile[(j + u) * F + c];
+                    s = fma(d, d, s);
+                }
+                acc[u] += sqrt(s);
+            }
+        }
+        for (; j < cnt; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < F; ++c) {
+                const double d = xi[c] - tile[j * F + c];
+                s = fma(d, d, s);
+            }
+            acc[0] += sqrt(s);
+        }
+    }
+    if (live) cost[p] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
+extern "C" int bf_kmedoids_cluster_cost_part(long long N, int f, int k, const double* X, const long long* perm,
+                                             const long long* seg, int part, int nparts, double* cost, void* stream) {
+    BF_CHECK_ARG(N > 0 && k > 0 && X && perm && seg && cost, BF_ERR_ARG, "bf_kmedoids_cluster_cost: bad argument");
+    BF_CHECK_ARG(f >= 1 && f <= KM_MAX_F, BF_ERR_SIZE, "bf_kmedoids_cluster_cost: f=%d outside 1..%d", f, KM_MAX_F);
+    BF_CHECK_ARG(nparts >= 1 && part >= 0 && part < nparts, BF_ERR_ARG, "bf_kmedoids_cluster_cost: bad part %d of %d", part, nparts);
+    // at most ceil(N / KM_THREADS) + k chunks in total; blocks past the last chunk exit
+    const long long max_chunks = (N + KM_THREADS - 1) / KM_THREADS + k;
+    const unsigned grid = (unsigned)((max_chunks + nparts - 1) / nparts);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (f) {
+#define BF_CASE(FF) case FF: bf_km_cost_kernel<FF><<<grid, KM_THREADS, 0, st>>>(k, X, perm, seg, part, nparts, cost); break;
+        BF_CASE(1) BF_CASE(2) BF_CASE(3) BF_CASE(4) BF_CASE(5) BF_CASE(6) BF_CASE(7) BF_CASE(8)
+#undef BF_CASE
+    }
+    BF_CHECK_LAUNCH("bf_kmedoids_cluster_cost");
+    return 0;
 }
 
 extern "C" int bf_kmedoids_cluster_cost(long long N, int f, int k, const double* X, const long long* perm,
                                         const long long* seg, double* cost, void* stream) {
-    BF_CHECK_ARG(N > 0 && k > 0 && X && perm && seg && cost, BF_ERR_ARG, "bf_kmedoids_cluster_cost: bad argument");
-    BF_CHECK_ARG(f >= 1 && f <= KM_MAX_F, BF_ERR_SIZE, "bf_kmedoids_cluster_cost: f=%d outside 1..%d", f, KM_MAX_F);
-    const unsigned grid = (unsigned)((N + KM_THREADS - 1) / KM_THREADS);
-    bf_km_cost_kernel<<<grid, KM_THREADS, 0, (cudaStream_t)stream>>>(N, f, k, X, perm, seg, cost);
-    BF_CHECK_LAUNCH("bf_kmedoids_cluster_cost");
-    return 0;
+    return bf_kmedoids_cluster_cost_part(N, f, k, X, perm, seg, 0, 1, cost, stream);
 }
 
 // one CTA per cluster: first argmin of the in-cluster costs; move the medoid only if strictly

@@ -115,3 +115,27 @@ def reduce_top2(t1, i1, t2, index_offset):
     others = torch.where(winner, torch.full_like(a, float("-inf")), a)
     second = torch.maximum(others.max(dim=0).values, c.max(dim=0).values)
     return best.to(dev), first.to(dev), second.to(dev)
+
+
+def gather_rows(local):
+    """Row-sharded vectors (k-medoids row sums): concatenation of the ranks' contiguous blocks."""
+    r, w = world()
+    if w == 1:
+        return local
+    out, _ = gather_sets(local, torch.zeros((local.numel(),), dtype=torch.int64, device=local.device))
+    return out
+
+
+def sum_parts(t):
+    """In-place sum over ranks of a vector whose every element is non-zero on exactly one rank (the
+    in-cluster cost parts of k-medoids); adding zeros is exact, so the result is rank-count invariant."""
+    r, w = world()
+    if w == 1:
+        return t
+    if dist.get_backend() == "gloo" and t.is_cuda:
+        h = t.cpu()
+        dist.all_reduce(h, op=dist.ReduceOp.SUM)
+        t.copy_(h)
+        return t
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t

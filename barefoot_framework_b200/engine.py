@@ -386,41 +386,62 @@ def zscore_targets(f_mean, f_var):
 
 # ---- k-medoids (util.py:38-49) -----------------------------------------------------------------
 def kmedoids_rowsum(X, row0=0, rows=None):
-    X = to_dev(X)
-    N, f = X.shape
+    Xd = to_dev(X)
+    N, f = Xd.shape
     rows = N - row0 if rows is None else rows
-    out = torch.empty((rows,), dtype=F64, device=X.device)
-    call("bf_kmedoids_rowsum", N, f, ptr(X), row0, rows, ptr(out), stream())
+    out = torch.empty((rows,), dtype=F64, device=Xd.device)
+    call("bf_kmedoids_rowsum", N, f, ptr(Xd), row0, rows, ptr(out), stream())
     return out
 
 
+def kmedoids_rowsum_sharded(X):
+    """Row sums of the implicit N x N distance matrix with the row blocks split over the ranks of a
+    torchrun job ("row blocks of the implicit D"); one all-gather of 8 N bytes.  Every
+    row sum is computed by exactly one rank with the same kernel, so the result does not depend on
+    the number of ranks."""
+    from . import dist as bdist
+    Xd = to_dev(X)
+    lo, hi = bdist.shard_range(Xd.shape[0])
+    return bdist.gather_rows(kmedoids_rowsum(Xd, lo, hi - lo))
+
+
 def kmedoids_fit(X, k, max_iter=300, rowsum=None):
-    """sklearn_extra KMedoids(k, random_state=0) defaults (oracle/kmedoids_shim.py): the
-    O(N^2) distance work runs on the device; the order-defining np.argpartition of the
-    heuristic init and the label sort run on host NumPy over N-vectors."""
+    """sklearn_extra KMedoids(k, random_state=0) defaults (oracle/kmedoids_shim.py).  All O(N^2) and
+    O(N k) work runs on the device: row sums, label assignment, the stable label sort
+    (bf_kmedoids_sort_labels), in-cluster costs and the medoid update; the host sees the N row sums
+    once (np.argpartition defines the order of the initial medoids) and one `changed` flag per
+    iteration.  Under torchrun the row sums and the in-cluster cost chunks are split over the ranks
+    and combined with one collective each (no other data crosses GPUs)."""
+    from . import dist as bdist
     Xd = to_dev(X)
     N, f = Xd.shape
     if k > N:
         raise ValueError("The number of medoids (%d) must be less than the number of samples %d." % (k, N))
+    rank, world = bdist.world()
     if rowsum is None:
-        rowsum = kmedoids_rowsum(Xd)
+        rowsum = kmedoids_rowsum_sharded(Xd) if world > 1 else kmedoids_rowsum(Xd)
     med = np.argpartition(rowsum.cpu().numpy(), k - 1)[:k].astype(np.int64)
     med_d = to_dev(med, torch.int64)
-    labels = torch.empty((N,), dtype=torch.int32, device=Xd.device)
-    cost = torch.empty((N,), dtype=F64, device=Xd.device)
-    changed = torch.zeros((1,), dtype=torch.int32, device=Xd.device)
+    dev = Xd.device
+    labels = torch.empty((N,), dtype=torch.int32, device=dev)
+    cost = torch.empty((N,), dtype=F64, device=dev)
+    perm = torch.empty((N,), dtype=torch.int64, device=dev)
+    seg = torch.empty((k + 1,), dtype=torch.int64, device=dev)
+    ws = torch.empty((_lib.load().bf_kmedoids_sort_workspace(N, k),), dtype=torch.uint8, device=dev)
+    changed = torch.zeros((1,), dtype=torch.int32, device=dev)
     st = stream()
     n_iter = 0
     for n_iter in range(max_iter):
         call("bf_kmedoids_assign", N, f, k, ptr(Xd), ptr(med_d), ptr(labels), st)
-        lab = labels.cpu().numpy()
-        perm = np.argsort(lab, kind="stable").astype(np.int64)
-        seg = np.zeros(k + 1, dtype=np.int64)
-        seg[1:] = np.cumsum(np.bincount(lab, minlength=k))
-        perm_d, seg_d = to_dev(perm, torch.int64), to_dev(seg, torch.int64)
-        call("bf_kmedoids_cluster_cost", N, f, k, ptr(Xd), ptr(perm_d), ptr(seg_d), ptr(cost), st)
+        call("bf_kmedoids_sort_labels", N, k, ptr(labels), ptr(perm), ptr(seg), ptr(ws), st)
+        if world > 1:
+            cost.zero_()
+            call("bf_kmedoids_cluster_cost_part", N, f, k, ptr(Xd), ptr(perm), ptr(seg), rank, world, ptr(cost), st)
+            bdist.sum_parts(cost)           # every position is written by exactly one rank: x + 0 = x
+        else:
+            call("bf_kmedoids_cluster_cost", N, f, k, ptr(Xd), ptr(perm), ptr(seg), ptr(cost), st)
         changed.zero_()
-        call("bf_kmedoids_update", N, k, ptr(perm_d), ptr(seg_d), ptr(cost), ptr(med_d), ptr(changed), st)
+        call("bf_kmedoids_update", N, k, ptr(perm), ptr(seg), ptr(cost), ptr(med_d), ptr(changed), st)
         if int(changed.item()) == 0:
             break
     call("bf_kmedoids_assign", N, f, k, ptr(Xd), ptr(med_d), ptr(labels), st)

@@ -177,6 +177,17 @@ int bf_kmedoids_assign(long long N, int f, int k, const double* X, const long lo
  * cost[p] = sum over q in the same segment of |x_perm[p] - x_perm[q]| (in segment order). */
 int bf_kmedoids_cluster_cost(long long N, int f, int k, const double* X, const long long* perm,
                              const long long* seg, double* cost, void* stream);
+/* The same for the chunks (128 consecutive positions of one cluster, numbered cluster-major) with
+ * chunk % nparts == part: the ranks of a multi-GPU job take one part each; positions of other parts
+ * are left untouched, so zero-filled cost arrays combine by addition. */
+int bf_kmedoids_cluster_cost_part(long long N, int f, int k, const double* X, const long long* perm,
+                                  const long long* seg, int part, int nparts, double* cost, void* stream);
+/* Stable counting sort of labels (np.where(labels == c)[0] for every c, util.py:42-45 and the
+ * alternate loop of KMedoids): perm [N] = rows ordered by (label, row), seg [k + 1] = offsets.
+ * workspace: bf_kmedoids_sort_workspace(N, k) bytes of device memory. */
+size_t bf_kmedoids_sort_workspace(long long N, int k);
+int bf_kmedoids_sort_labels(long long N, int k, const int32_t* labels, long long* perm, long long* seg,
+                            void* workspace, void* stream);
 /* Per cluster: first argmin of cost, and the alternate-method rule "move only if strictly
  * better than the current medoid".  medoid_idx is updated in place; changed[0] counts moves. */
 int bf_kmedoids_update(long long N, int k, const long long* perm, const long long* seg,

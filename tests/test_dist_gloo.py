@@ -83,6 +83,26 @@ def test_candidate_sharding_first_index_tie_rule():
         np.testing.assert_array_equal(g2, vals[np.arange(vals.shape[0]), order[:, 1]])
 
 
+def _rows_case(rank, world):
+    from barefoot_framework_b200 import dist as bd
+    N = 11
+    full = np.arange(N, dtype=np.float64) * 1.5 + 0.25
+    a, b = bd.shard_range(N)
+    rows = bd.gather_rows(torch.tensor(full[a:b]))
+    part = np.zeros(N)
+    part[rank::world] = full[rank::world]                 # interleaved parts, zeros elsewhere
+    summed = bd.sum_parts(torch.tensor(part))
+    return rows.numpy(), summed.numpy(), full
+
+
+def test_row_blocks_and_cost_parts_combine_exactly():
+    """k-medoids exchanges: row-sum blocks concatenate in row order; in-cluster cost
+    parts (each element non-zero on one rank) add up bit-exactly."""
+    for rows, summed, full in _run(_rows_case):
+        np.testing.assert_array_equal(rows, full)
+        np.testing.assert_array_equal(summed, full)
+
+
 def test_single_process_is_identity():
     from barefoot_framework_b200 import dist as bd
     v, i = torch.tensor([1.0, 2.0]), torch.tensor([3, 4])
@@ -123,3 +143,28 @@ def test_tm_stage_sharded_over_two_ranks_matches_reference():
         for opt, (v, i, rv, ri) in out.items():
             np.testing.assert_array_equal(i, ri, err_msg=opt)
             np.testing.assert_allclose(v, rv, rtol=1e-8, atol=1e-11, err_msg=opt)
+
+
+def _kmedoids_sharded(rank, world):
+    """Two ranks (gloo; both on cuda:0) split the row sums and the in-cluster cost chunks."""
+    from barefoot_framework_b200 import engine
+    rng = np.random.default_rng(5)
+    N, k = 3001, 6
+    X = np.column_stack([np.exp(rng.normal(size=N)), rng.permutation(10 * N)[:N].astype(float),
+                         rng.integers(0, 3, size=N).astype(float)])
+    med, labels, n_iter = engine.kmedoids_fit(X, k)
+    rs = engine.kmedoids_rowsum_sharded(X).cpu().numpy()
+    return med, labels, n_iter, rs, X, k
+
+
+@pytest.mark.gpu
+def test_kmedoids_sharded_over_two_ranks_matches_oracle():
+    from oracle.kmedoids_shim import KMedoids, pairwise_euclidean
+    res = _run(_kmedoids_sharded)
+    med, labels, n_iter, rs, X, k = res[0]
+    km = KMedoids(n_clusters=k, random_state=0).fit(X)
+    for (m, l, it, r, _, _) in res:
+        np.testing.assert_array_equal(m, km.medoid_indices_)
+        np.testing.assert_array_equal(l, km.labels_)
+        assert it == km.n_iter_
+        np.testing.assert_allclose(r, pairwise_euclidean(X).sum(axis=1), rtol=1e-9)

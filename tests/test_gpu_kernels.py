@@ -272,6 +272,59 @@ def test_kmedoids_matches_oracle(eng, N, f, k):
     assert n_iter == km.n_iter_
 
 
+@pytest.mark.parametrize("N,k", [(1, 1), (1023, 3), (1024, 10), (5000, 1), (70001, 37)])
+def test_kmedoids_label_sort_is_stable(eng, N, k):
+    """bf_kmedoids_sort_labels == np.argsort(labels, kind="stable") and the cluster offsets;
+    empty clusters allowed (labels drawn from a subset)."""
+    import torch
+    from barefoot_framework_b200 import _lib
+    from barefoot_framework_b200._lib import call, ptr, stream
+    rng = np.random.default_rng(N + k)
+    lab = rng.integers(0, k, size=N).astype(np.int32)
+    if k > 2:
+        lab[lab == 1] = 0                                  # cluster 1 is empty
+    lab_d = eng.to_dev(lab, torch.int32)
+    perm = torch.empty((N,), dtype=torch.int64, device=lab_d.device)
+    seg = torch.empty((k + 1,), dtype=torch.int64, device=lab_d.device)
+    ws = torch.empty((_lib.load().bf_kmedoids_sort_workspace(N, k),), dtype=torch.uint8, device=lab_d.device)
+    call("bf_kmedoids_sort_labels", N, k, ptr(lab_d), ptr(perm), ptr(seg), ptr(ws), stream())
+    np.testing.assert_array_equal(perm.cpu().numpy(), np.argsort(lab, kind="stable"))
+    ref_seg = np.zeros(k + 1, dtype=np.int64)
+    ref_seg[1:] = np.cumsum(np.bincount(lab, minlength=k))
+    np.testing.assert_array_equal(seg.cpu().numpy(), ref_seg)
+
+
+@pytest.mark.parametrize("N,f,k,nparts", [(3000, 3, 7, 2), (3000, 2, 4, 8), (130, 3, 5, 3)])
+def test_kmedoids_cost_parts_add_up_to_whole(eng, N, f, k, nparts):
+    """The in-cluster costs computed part by part (one part per rank of a multi-GPU job) are bitwise
+    the single-call costs, and both equal the oracle's D[idx][:, idx].sum(axis=1) to rounding."""
+    import torch
+    from barefoot_framework_b200._lib import call, ptr, stream
+    from oracle.kmedoids_shim import pairwise_euclidean
+    rng = np.random.default_rng(N * f + k)
+    X = rng.normal(size=(N, f))
+    lab = rng.integers(0, k, size=N).astype(np.int32)
+    perm = np.argsort(lab, kind="stable").astype(np.int64)
+    seg = np.zeros(k + 1, dtype=np.int64)
+    seg[1:] = np.cumsum(np.bincount(lab, minlength=k))
+    Xd, perm_d, seg_d = eng.to_dev(X), eng.to_dev(perm, torch.int64), eng.to_dev(seg, torch.int64)
+    whole = torch.empty((N,), dtype=torch.float64, device=Xd.device)
+    call("bf_kmedoids_cluster_cost", N, f, k, ptr(Xd), ptr(perm_d), ptr(seg_d), ptr(whole), stream())
+    total = torch.zeros((N,), dtype=torch.float64, device=Xd.device)
+    for part in range(nparts):
+        piece = torch.zeros((N,), dtype=torch.float64, device=Xd.device)
+        call("bf_kmedoids_cluster_cost_part", N, f, k, ptr(Xd), ptr(perm_d), ptr(seg_d), part, nparts, ptr(piece), stream())
+        assert int(((piece != 0) & (total != 0)).sum().item()) == 0       # parts are disjoint
+        total += piece
+    assert torch.equal(total, whole)
+    D = pairwise_euclidean(X)
+    ref = np.empty(N)
+    for c in range(k):
+        idx = np.where(lab == c)[0]
+        ref[seg[c]:seg[c + 1]] = D[idx][:, idx].sum(axis=1)
+    np.testing.assert_allclose(whole.cpu().numpy(), ref, rtol=1e-9, atol=1e-9)
+
+
 @pytest.mark.parametrize("kern", ["SE", "M52"])
 @pytest.mark.parametrize("n,d,N", [(40, 10, 300), (300, 16, 700), (64, 9, 49), (900, 12, 100)])
 def test_posterior_high_dimensional_inputs(eng, kern, n, d, N):
