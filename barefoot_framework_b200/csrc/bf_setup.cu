@@ -3,6 +3,8 @@
 // george GP.compute -> scipy cholesky, and the cho_solve for alpha behind gpModel.py:47,53.
 // All matrices are np x np row-major, np = n rounded up to 32, padded with the identity so
 // every 32 x 32 block is full.
+#include <stdlib.h>
+
 #include "bf_common.cuh"
 
 // ---- K = amp k(X, X) + diag(yerr_eff^2) ------------------------------------------------------
@@ -274,22 +276,26 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_cholesky_rl_kernel(int n,
 #ifdef BF_PROFILE_SETUP
     long long prof_t_ = clock64();
 #endif
-    for (int kb = 0; kb < nb; ++kb) {
+    // Diagonal block kb sits in Ld: factor it, write L_kk, invert it into Li (warp 0 only).
+    auto factor_diag = [&](int kb) {
         const int r0 = 32 * kb;
-        // 1. diagonal block: factor and invert (warp 0)
-        if (warp == 0) {
+        const int b = rl_factor_block(Ld, rdiag, lane);
+        if (b && lane == 0 && bad == 0) bad = r0 + b;
 #pragma unroll 8
-            for (int j = 0; j < 32; ++j) Ld[j][lane] = A[(size_t)(r0 + j) * np + r0 + lane];   // coalesced rows
-            __syncwarp();
-            const int b = rl_factor_block(Ld, rdiag, lane);
-            if (b && lane == 0 && bad == 0) bad = r0 + b;
+        for (int j = 0; j < 32; ++j) A[(size_t)(r0 + j) * np + r0 + lane] = Ld[j][lane];
+        rl_invert_block(Ld, rdiag, Li, lane);
+    };
+    if (warp == 0) {
 #pragma unroll 8
-            for (int j = 0; j < 32; ++j) A[(size_t)(r0 + j) * np + r0 + lane] = Ld[j][lane];
-            rl_invert_block(Ld, rdiag, Li, lane);
-        }
-        __syncthreads();
-        BF_PROF_MARK(0);
-        // 2. panel column: P_i = A[i, k] L_kk^-T for the row blocks below, kept in shared memory
+        for (int j = 0; j < 32; ++j) Ld[j][lane] = A[(size_t)j * np + lane];                   // coalesced rows
+        __syncwarp();
+        factor_diag(0);
+    }
+    __syncthreads();
+    BF_PROF_MARK(0);
+    for (int kb = 0; kb < nb - 1; ++kb) {
+        const int r0 = 32 * kb;
+        // 1. panel column: P_i = A[i, k] L_kk^-T for the row blocks below, kept in shared memory
         for (int ib = kb + 1 + warp; ib < nb; ib += BF_RL_WARPS) {
             double c[4][4][2];
             rl_zero(c);
@@ -307,11 +313,15 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_cholesky_rl_kernel(int n,
         }
         __syncthreads();
         BF_PROF_MARK(1);
-        // 3. trailing update: A[i, j] -= P_i P_j^T for kb < j <= i (both operands in shared memory; the
-        //    old values are requested first so their L2 round trip overlaps the 64 DMMAs)
+        // 2. trailing update: A[i, j] -= P_i P_j^T for kb < j <= i (both operands in shared memory; the
+        //    old values are requested first so their L2 round trip overlaps the 64 DMMAs).  Look-ahead:
+        //    warp 0 updates the next diagonal block, keeps it in shared memory and factors it while the
+        //    other warps finish the rest of the update, so the serial 32 x 32 factorisation (a single-warp
+        //    dependency chain) is off the critical path whenever the update takes longer.
         const int m = nb - kb - 1;
         const int ntiles = m * (m + 1) / 2;
-        for (int q = warp; q < ntiles; q += BF_RL_WARPS) {
+        const int q_first = warp == 0 ? 0 : warp, q_step = warp == 0 ? ntiles : BF_RL_WARPS - 1;
+        for (int q = q_first; q < ntiles; q += q_step) {
             int ii = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
             while (ii * (ii + 1) / 2 > q) --ii;
             while ((ii + 1) * (ii + 2) / 2 <= q) ++ii;
@@ -325,15 +335,28 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_cholesky_rl_kernel(int n,
             double c[4][4][2];
             rl_zero(c);
             rl_tile_smem(c, panel + (size_t)(32 * ii) * BF_RL_PLD, panel + (size_t)(32 * jj) * BF_RL_PLD, BF_RL_PLD, 8);
+            if (q == 0) {                       // warp 0: the next diagonal block goes straight to the factorisation
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
+                for (int t = 0; t < 4; ++t)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    double2 v = old[t][u];
-                    v.x -= c[t][u][0];
-                    v.y -= c[t][u][1];
-                    *reinterpret_cast<double2*>(dst0 + (size_t)(8 * t) * np + 8 * u) = v;
-                }
+                    for (int u = 0; u < 4; ++u) {
+                        const int rr = 8 * t + (lane >> 2), cc = 8 * u + 2 * (lane & 3);
+                        Ld[rr][cc] = old[t][u].x - c[t][u][0];
+                        Ld[rr][cc + 1] = old[t][u].y - c[t][u][1];
+                    }
+                __syncwarp();
+                factor_diag(kb + 1);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        double2 v = old[t][u];
+                        v.x -= c[t][u][0];
+                        v.y -= c[t][u][1];
+                        *reinterpret_cast<double2*>(dst0 + (size_t)(8 * t) * np + 8 * u) = v;
+                    }
+            }
         }
         __syncthreads();
         BF_PROF_MARK(2);
@@ -444,6 +467,197 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_factor_finish_rl_kernel(
         }
     }
     BF_PROF_MARK(6);
+}
+
+// ---- L^-1 by independent column groups (every column of the inverse is its own forward substitution) ----
+// One CTA per (block column J, pair of 8-column groups): W warps, each owning 8 columns of L^-1 for all
+// row blocks I >= J.  x_J = Linv_JJ[:, cols]; x_I = -Linv_II (sum_{K=J}^{I-1} L[I,K] x_K).  The A tiles
+// (L[I,K], then Linv_II) are the same for every warp of the CTA and stream from L2 through a cp.async ring;
+// the x_K history stays in shared memory in DMMA B-fragment order.  4 nb CTAs per set instead of one, so a
+// single 500 x 500 inverse takes tens of microseconds instead of the 0.55 ms one SM needs for n^3/3 flop.
+#define BF_COLS_RING 8
+#define BF_COLS_TLD 36
+
+__device__ __forceinline__ void bf_cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void bf_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NKEEP>
+__device__ __forceinline__ void bf_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NKEEP) : "memory"); }
+
+// inverses of the diagonal blocks (warp 0) and zeros right of the diagonal (the other warps): grid (nb, S)
+__global__ void __launch_bounds__(128) bf_diag_inverse_kernel(int np, const double* __restrict__ Lall,
+                                                              double* __restrict__ Linv_all,
+                                                              double* __restrict__ packed_all, size_t packed_stride) {
+    __shared__ double Lw[32][33];
+    __shared__ double Lo[32][33];
+    const int kb = blockIdx.x, set = blockIdx.y, nb = np / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double* L = Lall + (size_t)set * np * np;
+    double* Linv = Linv_all + (size_t)set * np * np;
+    double* packed = packed_all + (size_t)set * packed_stride;
+    const int r0 = 32 * kb;
+    if (warp == 0) {
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) Lw[j][lane] = L[(size_t)(r0 + j) * np + r0 + lane];
+        __syncwarp();
+        rl_invert_block(Lw, nullptr, Lo, lane);
+        __syncwarp();
+        for (int i = 0; i < 32; ++i) {
+            const double v = Lo[i][lane];
+            Linv[(size_t)(r0 + i) * np + r0 + lane] = v;
+            packed[bf_linv_elem_off(r0 + i, r0 + lane)] = v;
+        }
+    } else {
+        const int width = np - r0 - 32;                 // doubles right of the diagonal block, per row
+        for (int e = threadIdx.x - 32; e < 32 * (width / 2); e += 96) {
+            const int i = e / (width / 2), j2 = (e - i * (width / 2)) * 2;
+            *reinterpret_cast<double2*>(Linv + (size_t)(r0 + i) * np + r0 + 32 + j2) = make_double2(0.0, 0.0);
+        }
+    }
+}
+
+// grid (4 nb, S): CTA = (block column J, 8-column group a); warp w owns rows 8w..8w+7 of every row block
+__global__ void __launch_bounds__(128) bf_linv_cols_kernel(int np, const double* __restrict__ Lall,
+                                                          double* __restrict__ Linv_all,
+                                                          double* __restrict__ packed_all, size_t packed_stride) {
+    extern __shared__ __align__(16) double cs_sm[];
+    constexpr int TLD = BF_COLS_TLD, RING = BF_COLS_RING;
+    const int nb = np / 32;
+    const int J = blockIdx.x >> 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = lane >> 2, kk = lane & 3;
+    const int c0 = 32 * J + 8 * (blockIdx.x & 3);              // this CTA's 8 columns
+    const int set = blockIdx.y;
+    const double* L = Lall + (size_t)set * np * np;
+    double* Linv = Linv_all + (size_t)set * np * np;
+    double* packed = packed_all + (size_t)set * packed_stride;
+    double* ring = cs_sm;                                       // RING x 32 x TLD
+    double* xh = ring + RING * 32 * TLD;                        // nb blocks of 32 x 8 (B-fragment order), + scratch
+    double* sbuf = xh + (size_t)nb * 256;
+
+    const int rows_below = nb - 1 - J;
+    const int M = rows_below * (rows_below + 3) / 2;            // sum_{I = J+1}^{nb-1} (I - J + 1) tiles
+    if (M == 0) return;
+    // x_J: these columns of the diagonal-block inverse (written by bf_diag_inverse_kernel)
+    for (int e = threadIdx.x; e < 256; e += 128) xh[e] = Linv[(size_t)(32 * J + (e >> 3)) * np + c0 + (e & 7)];
+
+    int pI = J + 1, pK = J;                                     // next tile to request; K == I means Linv_II
+    auto request = [&](int slot) {
+        const double* src = (pK < pI ? L : Linv) + (size_t)(32 * pI) * np + 32 * pK;
+        double* dst = ring + (size_t)slot * 32 * TLD;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = threadIdx.x + 128 * q, row = e >> 4, ch = e & 15;
+            bf_cp_async16(dst + row * TLD + 2 * ch, src + (size_t)row * np + 2 * ch);
+        }
+        if (pK < pI) ++pK; else { ++pI; pK = J; }
+    };
+    for (int t = 0; t < RING - 1; ++t) {
+        if (t < M) request(t);
+        bf_cp_async_commit();
+    }
+    double acc[8][2];                                           // one chain per k-step: a tile adds one DMMA to each
+#pragma unroll
+    for (int h = 0; h < 8; ++h) acc[h][0] = acc[h][1] = 0.0;
+    auto acc_sum = [&](int q) {
+        return ((acc[0][q] + acc[1][q]) + (acc[2][q] + acc[3][q])) + ((acc[4][q] + acc[5][q]) + (acc[6][q] + acc[7][q]));
+    };
+    int I = J + 1, K = J;
+    for (int t = 0; t < M; ++t) {
+        bf_cp_async_wait<RING - 2>();
+        __syncthreads();                                        // tile t and x_{I-1} visible; slot (t - 1) % RING free
+        if (t + RING - 1 < M) request((t + RING - 1) % RING);
+        bf_cp_async_commit();
+        const double* A = ring + (size_t)(t % RING) * 32 * TLD + (8 * warp + r) * TLD + kk;
+        if (K < I) {
+            const double* B = xh + (size_t)(K - J) * 256 + kk * 8 + r;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) bf_dmma(acc[ks][0], acc[ks][1], A[4 * ks], B[ks * 32]);
+            ++K;
+        } else {
+            // s = sum_K L[I,K] x_K is complete: x_I = -Linv_II s
+            *reinterpret_cast<double2*>(sbuf + (8 * warp + r) * 8 + 2 * kk) = make_double2(acc_sum(0), acc_sum(1));
+#pragma unroll
+            for (int h = 0; h < 8; ++h) acc[h][0] = acc[h][1] = 0.0;
+            __syncthreads();
+            const double* B = sbuf + kk * 8 + r;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) bf_dmma(acc[ks][0], acc[ks][1], A[4 * ks], B[ks * 32]);
+            const double2 v = make_double2(-acc_sum(0), -acc_sum(1));
+#pragma unroll
+            for (int h = 0; h < 8; ++h) acc[h][0] = acc[h][1] = 0.0;
+            const int i = 32 * I + 8 * warp + r, j = c0 + 2 * kk;
+            *reinterpret_cast<double2*>(xh + (size_t)(I - J) * 256 + (8 * warp + r) * 8 + 2 * kk) = v;
+            *reinterpret_cast<double2*>(Linv + (size_t)i * np + j) = v;
+            packed[bf_linv_elem_off(i, j)] = v.x;
+            packed[bf_linv_elem_off(i, j + 1)] = v.y;
+            ++I;
+            K = J;
+        }
+    }
+}
+
+// alpha = Linv^T (Linv y): one CTA of 32 warps per set.  t = Linv y: warp per row.  alpha_j = sum_i Linv[i][j] t_i:
+// warp w sums the rows i = w (mod 32) for all columns (lane = column within a 32-column block), then the 32
+// partial rows are added in warp order.
+#define BF_ALPHA_MAX_NB 23              // np <= BF_SETUP_RL_MAX_NP
+#define BF_ALPHA_WARPS 16
+__global__ void __launch_bounds__(32 * BF_ALPHA_WARPS) bf_alpha_kernel(int n, int np, const double* __restrict__ Linv_all,
+                                                                       const double* __restrict__ y, long long y_stride,
+                                                                       double* __restrict__ alpha_all) {
+    extern __shared__ __align__(16) double al_sm[];
+    double* tvec = al_sm;                                       // np
+    double* part = al_sm + np;                                  // BF_ALPHA_WARPS x np
+    const int set = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nb = np / 32;
+    const double* Linv = Linv_all + (size_t)set * np * np;
+    const double* yv = y + (size_t)set * y_stride;
+    double* ys = part;                                          // y staged in shared memory (part is free until phase 2)
+    for (int j = threadIdx.x; j < np; j += 32 * BF_ALPHA_WARPS) ys[j] = j < n ? yv[j] : 0.0;
+    __syncthreads();
+    for (int i = warp; i < np; i += BF_ALPHA_WARPS) {
+        // all loads of the row are issued before the (order-preserving) FMA chain
+        double v[BF_ALPHA_MAX_NB];
+        const double* row = Linv + (size_t)i * np + lane;
+#pragma unroll
+        for (int cb = 0; cb < BF_ALPHA_MAX_NB; ++cb) v[cb] = (i < n && 32 * cb + lane <= i) ? row[32 * cb] : 0.0;
+        double s = 0.0;
+#pragma unroll
+        for (int cb = 0; cb < BF_ALPHA_MAX_NB; ++cb)
+            if (32 * cb + lane <= i) s = fma(v[cb], ys[32 * cb + lane], s);
+#pragma unroll
+        for (int mm = 16; mm > 0; mm >>= 1) s += __shfl_xor_sync(0xffffffffu, s, mm);
+        if (lane == 0) tvec[i] = s;
+    }
+    __syncthreads();
+    double acc[BF_ALPHA_MAX_NB];
+#pragma unroll
+    for (int cb = 0; cb < BF_ALPHA_MAX_NB; ++cb) acc[cb] = 0.0;
+    for (int i = warp; i < np; i += BF_ALPHA_WARPS) {
+        const int ib = i >> 5;
+        const double ti = (i < n) ? tvec[i] : 0.0;
+        const double* row = Linv + (size_t)i * np + lane;
+#pragma unroll
+        for (int cb = 0; cb < BF_ALPHA_MAX_NB; ++cb)
+            if (cb <= ib) acc[cb] = fma(row[32 * cb], ti, acc[cb]);     // zeros above the diagonal inside block ib
+    }
+#pragma unroll
+    for (int cb = 0; cb < BF_ALPHA_MAX_NB; ++cb)
+        if (cb < nb) part[(size_t)warp * np + 32 * cb + lane] = acc[cb];
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += 32 * BF_ALPHA_WARPS) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < BF_ALPHA_WARPS; ++w) s += part[(size_t)w * np + j];
+        alpha_all[(size_t)set * n + j] = s;
+    }
+}
+
+static size_t linv_cols_smem_bytes(int np) {
+    const int nb = np / 32;
+    return sizeof(double) * ((size_t)BF_COLS_RING * 32 * BF_COLS_TLD + (size_t)(nb + 1) * 256);
 }
 
 // ---- batched Cholesky (left-looking, 32-wide panels, one CTA per matrix) ----------------------
@@ -686,12 +900,42 @@ __global__ void __launch_bounds__(BF_THREADS) bf_factor_finish_kernel(
     }
 }
 
+// Sets up to which bf_factor_finish uses the column-group kernels (BF_SETUP_COLS_MAX_SETS overrides; measurement aid)
+static int bf_setup_cols_max_sets() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("BF_SETUP_COLS_MAX_SETS");
+        v = e ? atoi(e) : 96;
+    }
+    return v;
+}
+
 extern "C" int bf_factor_finish(int n, int S, const double* L, const double* y, long long y_stride,
                                 double* Linv, double* linv_packed, double* alpha, void* stream) {
     BF_CHECK_ARG(n > 0 && S >= 0 && L && Linv && linv_packed, BF_ERR_ARG, "bf_factor_finish: bad argument");
     BF_CHECK_ARG(!alpha || y, BF_ERR_ARG, "bf_factor_finish: alpha requested without y");
     if (S == 0) return 0;
     const int np = bf_padded_n(n);
+    if (np <= BF_SETUP_RL_MAX_NP && S <= bf_setup_cols_max_sets()) {
+        // few sets: spread every inverse over 4 nb CTAs
+        const size_t smem_c = linv_cols_smem_bytes(np);
+        const size_t smem_a = sizeof(double) * (size_t)(BF_ALPHA_WARPS + 1) * np;
+        cudaError_t e3 = cudaFuncSetAttribute(bf_linv_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+        if (e3 == cudaSuccess)
+            e3 = cudaFuncSetAttribute(bf_alpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+        if (e3 != cudaSuccess) {
+            bf_set_error("bf_factor_finish: cudaFuncSetAttribute: %s", cudaGetErrorString(e3));
+            return (int)e3;
+        }
+        cudaStream_t st = (cudaStream_t)stream;
+        const int nb = np / 32;
+        const size_t pstride = bf_linv_packed_doubles(n);
+        bf_diag_inverse_kernel<<<dim3(nb, S), 128, 0, st>>>(np, L, Linv, linv_packed, pstride);
+        bf_linv_cols_kernel<<<dim3(4 * nb, S), 128, smem_c, st>>>(np, L, Linv, linv_packed, pstride);
+        if (alpha) bf_alpha_kernel<<<S, 32 * BF_ALPHA_WARPS, smem_a, st>>>(n, np, Linv, y, y_stride, alpha);
+        BF_CHECK_LAUNCH("bf_factor_finish");
+        return 0;
+    }
     if (np <= BF_SETUP_RL_MAX_NP) {
         const size_t w_sz = (size_t)32 * (np + 4), scratch = (size_t)BF_RL_WARPS * 64 * 33;
         const size_t smem_rl = sizeof(double) * (np + (w_sz > scratch ? w_sz : scratch));

@@ -81,6 +81,32 @@ def test_setup_kernels(eng, kern, n, d):
         assert np.abs(alpha[h] - g.alpha).max() <= 1e-9 * np.abs(g.alpha).max()
 
 
+@pytest.mark.parametrize("n,d", [(31, 2), (64, 3), (333, 6), (500, 6), (700, 4)])
+def test_inverse_column_groups_agree_with_one_cta_per_set(eng, n, d):
+    """bf_factor_finish has two schedules: a few sets are inverted by independent column groups spread
+    over many SMs, many sets by one CTA each.  Same L in, the same L^-1 (to rounding) and alpha out."""
+    rng = np.random.default_rng(n + d)
+    X, y, _ = make_problem(rng, n, d, 4)
+    l = rng.uniform(0.15, 0.8, size=(2, d))
+    sf = rng.uniform(0.5, 3.0, size=2)
+    few = eng.build_factors("M52", X, y, l ** 2, sf, 0.05, keep_dense=True)
+    many_hp = np.tile(np.arange(2, dtype=np.int32), 33)                  # 66 sets > the column-group limit
+    many = eng.build_factors("M52", X, y, l ** 2, sf, 0.05, set_hp=many_hp, keep_dense=True)
+    assert np.array_equal(few.L.cpu().numpy(), many.L.cpu().numpy()[:2])
+    a, b = few.Linv.cpu().numpy(), many.Linv.cpu().numpy()
+    for h in range(2):
+        Lh = few.L.cpu().numpy()[h]
+        for got in (a[h], b[h], b[64 + h]):
+            assert not np.triu(got, 1).any()
+            # residual of the defining equation, relative to |L^-1| |L|
+            res = np.abs(got @ Lh - np.eye(Lh.shape[0])).max()
+            assert res <= 1e-13 * np.abs(got).max() * np.abs(Lh).max() * Lh.shape[0]
+        assert np.abs(a[h] - b[h]).max() <= 1e-9 * np.abs(b[h]).max()
+        assert np.array_equal(unpack_linv(few.linv_packed.cpu().numpy()[h], n), a[h])
+        np.testing.assert_allclose(few.alpha.cpu().numpy()[h], many.alpha.cpu().numpy()[h], rtol=1e-8,
+                                   atol=1e-9 * np.abs(many.alpha.cpu().numpy()[h]).max())
+
+
 def test_cholesky_reports_non_positive_definite(eng):
     X = np.array([[0.1], [0.1], [0.5]])     # duplicated point, zero noise -> singular
     with pytest.raises(np.linalg.LinAlgError):
