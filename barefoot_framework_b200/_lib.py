@@ -31,6 +31,7 @@ SIGNATURES = {
     "bf_kernel_matrix": (c_i, [c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_p, c_p]),
     "bf_cholesky_batched": (c_i, [c_i, c_i, c_p, c_p, c_p]),
     "bf_factor_finish": (c_i, [c_i, c_i, c_p, c_p, c_ll, c_p, c_p, c_p, c_p]),
+    "bf_factor_finish_kernels": (c_i, [c_i, c_i, c_i]),
     "bf_gp_posterior": (c_i, [c_i, c_ll, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
                               c_p, c_p, c_i, c_i, c_d, c_d, c_d, c_p, c_p, c_p]),
     "bf_gp_solve_rows": (c_i, [c_i, c_ll, c_i, c_i, c_p, c_p, c_p, c_d, c_p, c_p, c_p, c_p, c_p, c_p]),
@@ -51,6 +52,7 @@ SIGNATURES = {
     "bf_kmedoids_sort_workspace": (c_sz, [c_ll, c_i]),
     "bf_kmedoids_sort_labels": (c_i, [c_ll, c_i, c_p, c_p, c_p, c_p, c_p]),
     "bf_kmedoids_update": (c_i, [c_ll, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "bf_group_best": (c_i, [c_ll, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "bf_affine": (c_i, [c_ll, c_p, c_d, c_d, c_p, c_p]),
     "bf_total_variance": (c_i, [c_ll, c_p, c_d, c_d, c_p, c_d, c_p, c_p]),
     "bf_zscore_targets": (c_i, [c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
@@ -110,5 +112,12 @@ def call(name, *args):
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise BarefootCudaError("%s failed (%d): %s" % (name, rc, lib.bf_last_error().decode()))
-    launches += _KERNELS_PER_CALL.get(name, 1)
+    if name == "bf_factor_finish":
+        launches += lib.bf_factor_finish_kernels(args[0], args[1], 1 if args[7] else 0)
+    elif name == "bf_kmedoids_sort_labels":
+        launches += 3
+    elif name == "bf_group_best":
+        launches += 4 if args[0] else 2
+    else:
+        launches += _KERNELS_PER_CALL.get(name, 1)
     return rc

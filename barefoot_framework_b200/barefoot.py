@@ -323,17 +323,17 @@ class barefoot():
         out = rom_stage_batch(self.reificationObj, self.xFused, hp, self.covFunc, x_test, new_mean,
                               self.acquisitionFunc, self.modelParam['costs'], self.maxTM,
                               iteration=self.currentIteration + 1, true_sample_count=self.sampleCount,
-                              kk_list=list(range(self.sampleCount)))
+                              kk_list=list(range(self.sampleCount)), as_arrays=True)
         return out
 
-    def _cluster_rom(self, kg_output):
-        """barefoot.py:2102-2172: per selected candidate x* keep, for every model that proposed it,
-        the row with the largest value; cluster the (value, x*, model) rows and return the original
-        rows of the chosen ones."""
+    @staticmethod
+    def _cluster_rows_host(kg_output, n_models):
+        """The reference's dictionary loop, verbatim semantics (barefoot.py:2110-2140); kept as the
+        statement of what `_cluster_rows` computes on the device and used by the tests."""
         best = {}
         for iii in range(kg_output.shape[0]):
             key, model = kg_output[iii, 2], int(kg_output[iii, 3])
-            entry = best.setdefault(key, {'models': [], 'nu': [1e-6] * len(self.ROM), 'row': [-1] * len(self.ROM)})
+            entry = best.setdefault(key, {'models': [], 'nu': [1e-6] * n_models, 'row': [-1] * n_models})
             if model in entry['models']:
                 if kg_output[iii, 1] > entry['nu'][model]:
                     entry['nu'][model], entry['row'][model] = kg_output[iii, 1], iii
@@ -341,7 +341,34 @@ class barefoot():
                 entry['models'].append(model)
                 entry['nu'][model], entry['row'][model] = kg_output[iii, 1], iii
         rows = [[entry['nu'][m], key, m, entry['row'][m]] for key, entry in best.items() for m in entry['models']]
-        med_input = np.array(rows, dtype=np.float64)
+        return np.array(rows, dtype=np.float64)
+
+    @staticmethod
+    def _cluster_rows(kg_output, n_models):
+        """barefoot.py:2110-2140 on the device (engine.group_best): rows [value, x*, model, row id] for
+        every (x*, model) pair that occurs, in the reference's order (x* by first appearance, models
+        by first appearance within x*).  Only the final ordering of the <= m N surviving rows is host work."""
+        from . import engine
+        values = np.asarray(kg_output[:, 1], dtype=np.float64)
+        xstar = np.asarray(kg_output[:, 2], dtype=np.float64)
+        model = np.asarray(kg_output[:, 3], dtype=np.int64)
+        xi = xstar.astype(np.int64)
+        if xi.size and (not np.array_equal(xi, xstar) or xi.min() < 0 or model.min() < 0 or model.max() >= n_models):
+            raise ValueError("clustering records need integer candidate indices and model indices < %d" % n_models)
+        n_x = int(xi.max()) + 1 if xi.size else 1
+        first, best_val, best_row = engine.group_best(xi * n_models + model, values, n_x * n_models)
+        first, best_val, best_row = first.cpu().numpy(), best_val.cpu().numpy(), best_row.cpu().numpy()
+        present = np.where(first < values.shape[0])[0]
+        key_first = first.reshape(n_x, n_models).min(axis=1)              # first appearance of x*
+        order = present[np.lexsort((first[present], key_first[present // n_models]))]
+        return np.column_stack([best_val[order], (order // n_models).astype(np.float64),
+                                (order % n_models).astype(np.float64), best_row[order].astype(np.float64)])
+
+    def _cluster_rom(self, kg_output):
+        """barefoot.py:2102-2172: per selected candidate x* keep, for every model that proposed it,
+        the row with the largest value; cluster the (value, x*, model) rows and return the original
+        rows of the chosen ones."""
+        med_input = self._cluster_rows(kg_output, len(self.ROM))
         if self.batch:
             k = self.batchSize if med_input.shape[0] > self.batchSize else med_input.shape[0]
             medoids = kmedoids_max(med_input[:, 0:3], k)
@@ -484,12 +511,11 @@ class barefoot():
                 # rows) and then indexes that list with the portfolio index (barefoot.py:1509-1521): the
                 # rows of work item `chosen` are clustered, and work items 0..5 feed the gain update.
                 # Reproduced as is.
-                items = [[out[k][s_] for k in range(6)] for s_ in range(len(out[0]))]
-                self._hedge_clusters = [x_test[self._cluster_rom(np.array(items[k]))[:, 2].astype(int), :]
-                                        for k in range(6)]
-                kg_output = np.array(items[chosen], dtype=object)
+                items = [np.stack([out[k][s_] for k in range(6)]) for s_ in range(6)]
+                self._hedge_clusters = [x_test[self._cluster_rom(items[k])[:, 2].astype(int), :] for k in range(6)]
+                kg_output = items[chosen]
             else:
-                kg_output = np.array(out, dtype=object)
+                kg_output = out
             medoid_out = self._cluster_rom(kg_output)
             model_cost = time() - self.timeCheck
             self.timeCheck = time()

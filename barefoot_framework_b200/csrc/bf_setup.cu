@@ -910,6 +910,12 @@ static int bf_setup_cols_max_sets() {
     return v;
 }
 
+extern "C" int bf_factor_finish_kernels(int n, int S, int with_alpha) {
+    const int np = bf_padded_n(n);
+    if (np <= BF_SETUP_RL_MAX_NP && S <= bf_setup_cols_max_sets()) return with_alpha ? 3 : 2;
+    return 1;
+}
+
 extern "C" int bf_factor_finish(int n, int S, const double* L, const double* y, long long y_stride,
                                 double* Linv, double* linv_packed, double* alpha, void* stream) {
     BF_CHECK_ARG(n > 0 && S >= 0 && L && Linv && linv_packed, BF_ERR_ARG, "bf_factor_finish: bad argument");

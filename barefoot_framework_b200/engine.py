@@ -69,6 +69,11 @@ def ucb_kt(ndim, iteration):
     return float(np.sqrt(0.2 * beta))
 
 
+def linv_packed_doubles(n):
+    """Doubles of the packed tensor-core operand of one n x n factor (bf_linv_packed_doubles)."""
+    return int(_lib.load().bf_linv_packed_doubles(int(n)))
+
+
 class GPFactors:
     """Factorised GPs sharing the training inputs X: one "set" per hyper-parameter
     set (and, in the ROM stage, per fantasy point)."""
@@ -446,3 +451,24 @@ def kmedoids_fit(X, k, max_iter=300, rowsum=None):
             break
     call("bf_kmedoids_assign", N, f, k, ptr(Xd), ptr(med_d), ptr(labels), st)
     return med_d.cpu().numpy(), labels.cpu().numpy().astype(np.int64), n_iter + 1
+
+
+def group_best(keys, values, n_groups):
+    """barefoot.__kg_calc_clustering's dictionary loop (barefoot.py:2102-2140) for all records at once:
+    per key the reference's in-order "first strict maximum".  keys [R] int64 in [0, n_groups),
+    values [R].  Returns device tensors (first_row [G], best_val [G], best_row [G]); empty groups have
+    first_row == R and best_row == -1."""
+    dev = device()
+    k = keys if isinstance(keys, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(keys, dtype=np.int64))
+    k = k.to(device=dev, dtype=torch.int64).contiguous()
+    v = to_dev(values)
+    R, G = k.numel(), int(n_groups)
+    first = torch.empty((G,), dtype=torch.int64, device=dev)
+    best_val = torch.empty((G,), dtype=F64, device=dev)
+    best_row = torch.empty((G,), dtype=torch.int64, device=dev)
+    bad = torch.zeros((1,), dtype=torch.int32, device=dev)
+    call("bf_group_best", R, G, ptr(k) if R else None, ptr(v) if R else None, ptr(first), ptr(best_val),
+         ptr(best_row), ptr(bad), stream())
+    if int(bad.item()):
+        raise ValueError("group_best: %d key(s) outside [0, %d)" % (int(bad.item()), G))
+    return first, best_val, best_row

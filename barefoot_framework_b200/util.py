@@ -142,12 +142,14 @@ def fused_calculate(param):
 # ROM stage: calculate_* for the (jj, kk, mm) grid (util.py:216-886)
 # ---------------------------------------------------------------------------------------------
 def rom_stage_batch(model, x_fused, hp_sets, kernel, x_test, new_mean, acq, cost, curr_max,
-                    iteration=1, true_sample_count=None, jj_list=None, kk_list=None):
+                    iteration=1, true_sample_count=None, jj_list=None, kk_list=None, as_arrays=False,
+                    max_bytes_in_flight=16 << 30):
     """The ROM-stage grid of barefoot.py:1001-1073: for every model jj, fantasy point kk and
     hyper-parameter set mm, update ROM jj with (x_test[kk], new_mean[jj][kk]), rebuild the fused
     GP and evaluate `acq` over x_test.  Returns the rows [max fused mean, value / cost[jj], x*,
     jj, kk, mm] in the reference's loop order (Greedy is not divided by the cost, util.py:876).
     For "Hedge" returns six such row lists in the portfolio order [KG, TS, EI, Greedy, PI, UCB].
+    as_arrays=True returns float64 arrays [G * H, 6 (+ 2 d for Greedy)] instead of lists of rows.
 
     The fused targets of one (jj, kk) do not depend on mm; the H fused GPs of every (jj, kk)
     are factorised and swept together (one set per (jj, kk, mm))."""
@@ -159,47 +161,74 @@ def rom_stage_batch(model, x_fused, hp_sets, kernel, x_test, new_mean, acq, cost
     M = N if true_sample_count is None else int(true_sample_count)
     jj_list = list(range(model.num_models)) if jj_list is None else list(jj_list)
     kk_list = list(range(N)) if kk_list is None else list(kk_list)
-    zs, zerrs, stats, keys = [], [], [], []
-    for jj in jj_list:
-        for kk in kk_list:
+    hedge = acq == "Hedge"
+    names = _HEDGE_ORDER if hedge else [acq if acq in ("KG", "TS", "EI", "PI", "UCB") else "Greedy"]
+    keys = [(jj, kk) for jj in jj_list for kk in kk_list]
+    G = len(keys)
+    # The factors of one set take ~8 F^2 / 2 bytes (1 MB at F = 500): the (jj, kk) groups are processed in
+    # chunks of at most `max_sets_in_flight` sets so the literal ROM stage of the reference (3 models x 50
+    # candidates x 1000 hyper-parameter sets = 150000 fused GPs, 159 GB of factors) fits any budget.
+    F = np.asarray(x_fused).shape[0]
+    per_set = 8 * (engine.linv_packed_doubles(F) + 3 * F)
+    groups_per_chunk = max(1, int(max_bytes_in_flight // (per_set * H)))
+    parts = {nm: ([], []) for nm in names}
+    parts["max_mean"] = []
+    for g0 in range(0, G, groups_per_chunk):
+        chunk = keys[g0:g0 + groups_per_chunk]
+        zs, zerrs, stats = [], [], []
+        for (jj, kk) in chunk:
             m2 = _fantasy_copy(model, copy)
             m2.update_GP(np.expand_dims(x_test[kk], axis=0), np.expand_dims(np.array([new_mean[jj][kk]]), axis=0), jj)
             z, zerr, st = m2.fused_targets_device(x_fused)
             zs.append(z)
             zerrs.append(zerr)
             stats.append(st)
-            keys.append((jj, kk))
-    G = len(keys)
-    Z = torch.stack(zs).repeat_interleave(H, dim=0).contiguous()          # [G*H, F]
-    ZE = torch.stack(zerrs).repeat_interleave(H, dim=0).contiguous()
-    ST = torch.stack(stats)                                               # [G, 2] (mean, std)
-    scale = ST[:, 1].repeat_interleave(H).contiguous()
-    shift = ST[:, 0].repeat_interleave(H).contiguous()
-    set_hp = np.tile(np.arange(H, dtype=np.int32), G)
-    f = engine.build_factors(kernel, x_fused, Z, hp[:, 1:] ** 2, hp[:, 0], ZE, ndim=model.num_dim,
-                             set_hp=set_hp)
-    hedge = acq == "Hedge"
-    names = _HEDGE_ORDER if hedge else [acq if acq in ("KG", "TS", "EI", "PI", "UCB") else "Greedy"]
-    # calculate_GPHedge hands the variance to PI / UCB (util.py:764-789) and uses x_test.shape[0] for KG
-    r = _sweep(f, scale, shift, x_test, names, "TM" if hedge else "ROM", curr_max, iteration, XI_ROM,
-               M=(N if hedge else M))
-    rows = {nm: [] for nm in names}
-    s = 0
-    for (jj, kk) in keys:
-        for mm in range(H):
-            for nm in names:
-                val = r[nm][0][s]
-                if not (nm == "Greedy" and not hedge):
-                    val = val / cost[jj]
-                row = [r["max_mean"][s], val, int(r[nm][1][s]), jj, kk, mm]
-                if nm == "Greedy" and not hedge:
-                    # calculate_Greedy appends the coordinates of the maximum twice (util.py:878-884)
-                    row += list(x_test[int(r[nm][1][s])]) * 2
-                rows[nm].append(row)
-            s += 1
+        Gc = len(chunk)
+        Z = torch.stack(zs).repeat_interleave(H, dim=0).contiguous()          # [Gc*H, F]
+        ZE = torch.stack(zerrs).repeat_interleave(H, dim=0).contiguous()
+        ST = torch.stack(stats)                                               # [Gc, 2] (mean, std)
+        scale = ST[:, 1].repeat_interleave(H).contiguous()
+        shift = ST[:, 0].repeat_interleave(H).contiguous()
+        set_hp = np.tile(np.arange(H, dtype=np.int32), Gc)
+        f = engine.build_factors(kernel, x_fused, Z, hp[:, 1:] ** 2, hp[:, 0], ZE, ndim=model.num_dim,
+                                 set_hp=set_hp)
+        # calculate_GPHedge hands the variance to PI / UCB (util.py:764-789) and uses x_test.shape[0] for KG
+        rc = _sweep(f, scale, shift, x_test, names, "TM" if hedge else "ROM", curr_max, iteration, XI_ROM,
+                    M=(N if hedge else M))
+        for nm in names:
+            parts[nm][0].append(np.asarray(rc[nm][0], dtype=np.float64))
+            parts[nm][1].append(np.asarray(rc[nm][1], dtype=np.int64))
+        parts["max_mean"].append(np.asarray(rc["max_mean"], dtype=np.float64))
+        del f, Z, ZE
+    r = {nm: (np.concatenate(parts[nm][0]), np.concatenate(parts[nm][1])) for nm in names}
+    r["max_mean"] = np.concatenate(parts["max_mean"])
+    # rows [max fused mean, value / cost[jj], x*, jj, kk, mm] for every set, built as arrays (no Python
+    # loop over the G * H work items); set s = g * H + mm
+    jj_s = np.repeat(np.array([k_[0] for k_ in keys], dtype=np.int64), H)
+    kk_s = np.repeat(np.array([k_[1] for k_ in keys], dtype=np.int64), H)
+    mm_s = np.tile(np.arange(H, dtype=np.int64), G)
+    cost_s = np.asarray(cost, dtype=np.float64)[jj_s]
+    rows = {}
+    for nm in names:
+        val = np.asarray(r[nm][0], dtype=np.float64)
+        idx = np.asarray(r[nm][1], dtype=np.int64)
+        if not (nm == "Greedy" and not hedge):
+            val = val / cost_s
+        cols = [np.asarray(r["max_mean"], dtype=np.float64), val, idx.astype(np.float64), jj_s.astype(np.float64),
+                kk_s.astype(np.float64), mm_s.astype(np.float64)]
+        if nm == "Greedy" and not hedge:
+            # calculate_Greedy appends the coordinates of the maximum twice (util.py:878-884)
+            cols += [x_test[idx], x_test[idx]]
+        rows[nm] = np.column_stack(cols)
+    if as_arrays:
+        return [rows[nm] for nm in names] if hedge else rows[names[0]]
+
+    def as_lists(a):
+        # the reference's work items return Python lists with int indices (util.py:241,265-266)
+        return [[row[0], row[1], int(row[2]), int(row[3]), int(row[4]), int(row[5])] + list(row[6:]) for row in a.tolist()]
     if hedge:
-        return [rows[nm] for nm in names]
-    return rows[names[0]]
+        return [as_lists(rows[nm]) for nm in names]
+    return as_lists(rows[names[0]])
 
 
 def _fantasy_copy(model, copy):

@@ -86,6 +86,9 @@ int bf_cholesky_batched(int n, int S, double* K_inout_L, int32_t* info, void* st
  * y is per set (y_stride = n) or shared (y_stride = 0). */
 int bf_factor_finish(int n, int S, const double* L, const double* y, long long y_stride,
                      double* Linv, double* linv_packed, double* alpha, void* stream);
+/* Kernels one bf_factor_finish call launches: 1 (one CTA per set) or, for a few sets, 3 (diagonal
+ * block inverses; column groups of L^-1 spread over 4 np/32 CTAs per set; alpha). */
+int bf_factor_finish_kernels(int n, int S, int with_alpha);
 
 /* ---- (1)+(2)+(4) posterior + elementwise acquisitions: gpModel.py:50-54,
  * reificationFusion.py:189-206, acquisitionFunc.py:98-214 ------------------------------------ */
@@ -192,6 +195,16 @@ int bf_kmedoids_sort_labels(long long N, int k, const int32_t* labels, long long
  * better than the current medoid".  medoid_idx is updated in place; changed[0] counts moves. */
 int bf_kmedoids_update(long long N, int k, const long long* perm, const long long* seg,
                        const double* cost, long long* medoid_idx, int32_t* changed, void* stream);
+
+/* ---- clustering glue: barefoot.__kg_calc_clustering, barefoot.py:2102-2140 ---------------------- */
+/* Records r < R carry key[r] in [0, G) (selected candidate x* and model folded into one key) and
+ * value[r].  Per group, the reference's in-order scan: the first record sets (value, row), a later one
+ * replaces them only if strictly greater (NaN never replaces; a NaN first record stays).
+ * first_row[g] = first record of the group (R if empty), best_val[g] / best_row[g] = the kept pair
+ * (0 / -1 if empty).  bad_key[0] is incremented for every key outside [0, G) (zero it first). */
+int bf_group_best(long long R, long long G, const long long* key, const double* value,
+                  long long* first_row, double* best_val, long long* best_row, int32_t* bad_key,
+                  void* stream);
 
 /* ---- small on-device helpers for the fused-GP targets: reificationFusion.py:147-159 -------- */
 /* out[i] = a[i] * scale + shift */

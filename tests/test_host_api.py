@@ -272,3 +272,53 @@ def test_subprocess_worker_file_protocol(pkg, tmp_path):
         np.testing.assert_allclose(out[:, 0], ref[:, 0], rtol=1e-8, atol=1e-11)
     finally:
         os.chdir(cwd)
+
+
+def _records(rng, R, n_x, n_models, coarse, specials):
+    val = rng.normal(size=R)
+    if coarse:
+        val = np.round(val, 1)
+    if specials:
+        for special in (np.nan, 0.0, -0.0, np.inf, -np.inf):
+            val[rng.integers(0, R, size=max(1, R // 12))] = special
+    return np.column_stack([rng.normal(size=R), val, rng.integers(0, n_x, size=R).astype(float),
+                            rng.integers(0, n_models, size=R).astype(float), np.zeros(R), np.zeros(R)])
+
+
+@pytest.mark.parametrize("R,n_x,n_models,coarse,specials", [
+    (1, 4, 3, False, False), (50, 5, 3, True, False), (5000, 40, 3, True, True), (5000, 3000, 4, False, True),
+    (150000, 50, 3, True, True)])
+def test_cluster_rows_device_equals_reference_scan(pkg, R, n_x, n_models, coarse, specials):
+    """engine.group_best (bf_group_best) against the reference's dictionary loop (barefoot.py:2110-2140),
+    including exact ties (first row wins), NaN (never replaces; a NaN first record stays), signed zeros and
+    infinities; 150000 records is the literal ROM stage (3 models x 50 candidates x 1000 sets)."""
+    from barefoot_framework_b200.barefoot import barefoot
+    rng = np.random.default_rng(R + n_x)
+    rec = _records(rng, R, n_x, n_models, coarse, specials)
+    want = barefoot._cluster_rows_host(rec, n_models)
+    got = barefoot._cluster_rows(rec, n_models)
+    assert got.shape == want.shape
+    np.testing.assert_array_equal(got[:, 1:], want[:, 1:])
+    np.testing.assert_array_equal(got[:, 0], want[:, 0])               # NaN == NaN, -0.0 == 0.0 here
+    assert np.array_equal(np.signbit(got[:, 0]), np.signbit(want[:, 0]))
+
+
+def test_cluster_rom_matches_reference_golden(pkg):
+    """barefoot._cluster_rom (device grouping + device k-medoids) selects the rows the verbatim
+    barefoot.__kg_calc_clustering selects (tests/golden/cluster.npz, oracle/gen_cluster.py)."""
+    from barefoot_framework_b200.barefoot import barefoot
+    g = golden("cluster.npz")
+    for c in range(int(g["ncases"])):
+        rec, want = g[f"c{c}_records"], g[f"c{c}_selected"]
+        n_models, batch, bsz = [int(v) for v in g[f"c{c}_params"]]
+        obj = barefoot.__new__(barefoot)
+        obj.ROM, obj.batch, obj.batchSize = [None] * n_models, bool(batch), bsz
+        np.testing.assert_array_equal(obj._cluster_rom(rec), want, err_msg=f"case {c}")
+
+
+def test_group_best_rejects_keys_out_of_range(pkg):
+    from barefoot_framework_b200 import engine
+    with pytest.raises(ValueError):
+        engine.group_best(np.array([0, 7, 2]), np.array([1.0, 2.0, 3.0]), 5)
+    first, val, row = engine.group_best(np.zeros(0, dtype=np.int64), np.zeros(0), 3)
+    assert (first.cpu().numpy() == 0).all() and (row.cpu().numpy() == -1).all()

@@ -159,3 +159,21 @@ def test_kmedoids_max():
     np.testing.assert_array_equal(med3, g["med3"])
     med2, _ = fast.kmedoids_max(g["X2"], int(g["k2"]))
     np.testing.assert_array_equal(med2, g["med2"])
+
+
+def test_cluster_rows_restatement_matches_reference_clustering():
+    """barefoot._cluster_rows_host (the statement of what the device path computes) + the oracle
+    k-medoids reproduce the rows the verbatim barefoot.__kg_calc_clustering selects."""
+    from barefoot_framework_b200.barefoot import barefoot
+    g = golden("cluster.npz")
+    for c in range(int(g["ncases"])):
+        rec, want = g[f"c{c}_records"], g[f"c{c}_selected"]
+        n_models, batch, bsz = [int(v) for v in g[f"c{c}_params"]]
+        med_input = barefoot._cluster_rows_host(rec, n_models)
+        if batch:
+            k = bsz if med_input.shape[0] > bsz else med_input.shape[0]
+            medoids, _ = fast.kmedoids_max(med_input[:, 0:3], k)
+        else:
+            medoids = [np.where(med_input[:, 0] == np.max(med_input[:, 0]))[0][0]]
+        got = rec[[int(med_input[m, 3]) for m in medoids], :]
+        np.testing.assert_array_equal(got, want, err_msg=f"case {c}")
