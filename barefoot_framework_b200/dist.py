@@ -117,13 +117,26 @@ def reduce_top2(t1, i1, t2, index_offset):
     return best.to(dev), first.to(dev), second.to(dev)
 
 
-def gather_rows(local):
-    """Row-sharded vectors (k-medoids row sums): concatenation of the ranks' contiguous blocks."""
+def gather_rows(local, n_total=None):
+    """Row-sharded vectors (k-medoids row sums): concatenation of the ranks' contiguous shard_range
+    blocks.  With n_total given every rank knows all block sizes, so this is ONE all-gather of equally
+    padded blocks and no host synchronisation."""
     r, w = world()
     if w == 1:
         return local
-    out, _ = gather_sets(local, torch.zeros((local.numel(),), dtype=torch.int64, device=local.device))
-    return out
+    if n_total is None:
+        out, _ = gather_sets(local, torch.zeros((local.numel(),), dtype=torch.int64, device=local.device))
+        return out
+    dev = local.device
+    sizes = [shard_range(n_total, q, w) for q in range(w)]
+    m = max(b - a for a, b in sizes)
+    pad = torch.zeros((m,), dtype=local.dtype, device=local.device)
+    pad[: local.numel()] = local
+    pad = _comm(pad)
+    out = torch.empty((w * m,), dtype=local.dtype, device=pad.device)
+    dist.all_gather_into_tensor(out, pad)
+    out = out.view(w, m)
+    return torch.cat([out[q, : b - a] for q, (a, b) in enumerate(sizes)]).to(dev)
 
 
 def sum_parts(t):

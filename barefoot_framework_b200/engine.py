@@ -407,7 +407,7 @@ def kmedoids_rowsum_sharded(X):
     from . import dist as bdist
     Xd = to_dev(X)
     lo, hi = bdist.shard_range(Xd.shape[0])
-    return bdist.gather_rows(kmedoids_rowsum(Xd, lo, hi - lo))
+    return bdist.gather_rows(kmedoids_rowsum(Xd, lo, hi - lo), Xd.shape[0])
 
 
 def kmedoids_fit(X, k, max_iter=300, rowsum=None):
@@ -433,10 +433,14 @@ def kmedoids_fit(X, k, max_iter=300, rowsum=None):
     perm = torch.empty((N,), dtype=torch.int64, device=dev)
     seg = torch.empty((k + 1,), dtype=torch.int64, device=dev)
     ws = torch.empty((_lib.load().bf_kmedoids_sort_workspace(N, k),), dtype=torch.uint8, device=dev)
-    changed = torch.zeros((1,), dtype=torch.int32, device=dev)
+    # one `changed` counter per iteration, read back every `poll` iterations: an iteration that moves no
+    # medoid is a fixed point of the loop, so the iterations run past it change nothing and the reported
+    # count is the first iteration whose counter is zero (KMedoids.n_iter_)
+    changed = torch.zeros((max_iter,), dtype=torch.int32, device=dev)
     st = stream()
-    n_iter = 0
-    for n_iter in range(max_iter):
+    poll = 4 if N >= 20000 else 1
+    n_iter = max_iter
+    for it in range(max_iter):
         call("bf_kmedoids_assign", N, f, k, ptr(Xd), ptr(med_d), ptr(labels), st)
         call("bf_kmedoids_sort_labels", N, k, ptr(labels), ptr(perm), ptr(seg), ptr(ws), st)
         if world > 1:
@@ -445,12 +449,14 @@ def kmedoids_fit(X, k, max_iter=300, rowsum=None):
             bdist.sum_parts(cost)           # every position is written by exactly one rank: x + 0 = x
         else:
             call("bf_kmedoids_cluster_cost", N, f, k, ptr(Xd), ptr(perm), ptr(seg), ptr(cost), st)
-        changed.zero_()
-        call("bf_kmedoids_update", N, k, ptr(perm), ptr(seg), ptr(cost), ptr(med_d), ptr(changed), st)
-        if int(changed.item()) == 0:
-            break
+        call("bf_kmedoids_update", N, k, ptr(perm), ptr(seg), ptr(cost), ptr(med_d), changed[it:].data_ptr(), st)
+        if (it + 1) % poll == 0 or it + 1 == max_iter:
+            done = (changed[: it + 1] == 0).nonzero()
+            if done.numel():
+                n_iter = int(done[0].item()) + 1
+                break
     call("bf_kmedoids_assign", N, f, k, ptr(Xd), ptr(med_d), ptr(labels), st)
-    return med_d.cpu().numpy(), labels.cpu().numpy().astype(np.int64), n_iter + 1
+    return med_d.cpu().numpy(), labels.cpu().numpy().astype(np.int64), n_iter
 
 
 def group_best(keys, values, n_groups):

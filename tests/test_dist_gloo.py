@@ -89,6 +89,8 @@ def _rows_case(rank, world):
     full = np.arange(N, dtype=np.float64) * 1.5 + 0.25
     a, b = bd.shard_range(N)
     rows = bd.gather_rows(torch.tensor(full[a:b]))
+    rows_known = bd.gather_rows(torch.tensor(full[a:b]), N)      # one collective, sizes from shard_range
+    assert torch.equal(rows, rows_known)
     part = np.zeros(N)
     part[rank::world] = full[rank::world]                 # interleaved parts, zeros elsewhere
     summed = bd.sum_parts(torch.tensor(part))
