@@ -17,14 +17,14 @@ def world():
     return 0, 1
 
 
-def gather_host_sets(values, indices):
+def gather_host_sets(values, indices, n_total=None):
     """gather_sets for host arrays (numpy in, numpy out); identity in a single process."""
     r, w = world()
     if w == 1:
         return values, indices
     import numpy as np
     v, i = gather_sets(torch.as_tensor(np.ascontiguousarray(values, dtype=np.float64)),
-                       torch.as_tensor(np.ascontiguousarray(indices, dtype=np.int64)))
+                       torch.as_tensor(np.ascontiguousarray(indices, dtype=np.int64)), n_total)
     return v.cpu().numpy(), i.cpu().numpy()
 
 
@@ -46,13 +46,30 @@ def _comm(t):
     return t
 
 
-def gather_sets(values, indices):
+def gather_sets(values, indices, n_total=None):
     """Set-sharded stages: every rank holds (values [h_r], indices [h_r]) for its contiguous block of
-    hyper-parameter sets; returns the concatenation over ranks in set order on every rank."""
+    hyper-parameter sets; returns the concatenation over ranks in set order on every rank.  With
+    n_total (the number of sets before sharding with shard_range) every rank knows all block sizes and
+    the exchange is ONE all-gather of a padded [2, m] block (indices travel bit-cast to float64);
+    without it the sizes are exchanged first."""
     r, w = world()
     if w == 1:
         return values, indices
     dev = values.device
+    if n_total is not None:
+        sizes = [b - a for a, b in (shard_range(n_total, q, w) for q in range(w))]
+        assert values.numel() == sizes[r], "gather_sets: local block does not match shard_range"
+        m = max(sizes)
+        pack = torch.zeros((2, m), dtype=torch.float64, device=dev)
+        pack[0, : values.numel()] = values
+        pack[1, : indices.numel()] = indices.to(torch.int64).view(torch.float64)
+        pack = _comm(pack).view(-1)
+        out = torch.empty((w * 2 * m,), dtype=torch.float64, device=pack.device)
+        dist.all_gather_into_tensor(out, pack)
+        out = out.view(w, 2, m)
+        gv = torch.cat([out[q, 0, :s] for q, s in enumerate(sizes)])
+        gi = torch.cat([out[q, 1, :s] for q, s in enumerate(sizes)]).view(torch.int64)
+        return gv.to(dev), gi.to(dev)
     values, indices = _comm(values), _comm(indices)
     n_local = torch.tensor([values.numel()], dtype=torch.int64, device=values.device)
     sizes = [torch.zeros_like(n_local) for _ in range(w)]

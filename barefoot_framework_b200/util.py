@@ -120,7 +120,7 @@ def fused_calculate_batch(model, x_fused, hp_sets, kernel, x_test, curr_max, sam
     r = _sweep(f, scale, shift, x_test, [name], "TM", curr_max, iteration, xi)
     if deterministic:
         # hyper-parameter sets are sharded over the ranks of a torchrun job; only (value, index) travels
-        return bdist.gather_host_sets(*r[name])
+        return bdist.gather_host_sets(*r[name], n_total=hp.shape[0])
     return r[name]
 
 
@@ -331,7 +331,7 @@ def batch_acquisition_batch(modelGP, hp_sets, x_test, curr_max, acqFunc, iterati
     name = acqFunc if acqFunc in ("TS", "EI", "PI", "UCB") else "Greedy"
     r = _sweep(f, scale, shift, x_test, [name], "BATCH", curr_max, iteration, xi)
     if name != "TS":
-        return bdist.gather_host_sets(*r[name])
+        return bdist.gather_host_sets(*r[name], n_total=hp.shape[0])
     return r[name]
 
 

@@ -41,6 +41,8 @@ def _sets_case(rank, world):
     vals, idxs = rng.normal(size=H), rng.integers(0, 1000, size=H)
     a, b = bd.shard_range(H)
     v, i = bd.gather_sets(torch.tensor(vals[a:b]), torch.tensor(idxs[a:b]))
+    v1, i1 = bd.gather_sets(torch.tensor(vals[a:b]), torch.tensor(idxs[a:b]), n_total=H)    # single collective
+    assert torch.equal(v, v1) and torch.equal(i, i1)
     return (a, b), v.numpy(), i.numpy(), vals, idxs
 
 

@@ -76,6 +76,18 @@ def config_reification_kg(args, N, H, tag):
     model.fused_targets_device(x_fused)                                   # warm-up: module load, allocator
     engine.kg_diag(torch.randn(2, 64, dtype=torch.float64, device="cuda"), torch.rand(2, 64, dtype=torch.float64, device="cuda"))
     engine.reification(torch.randn(3, 64, dtype=torch.float64, device="cuda"), torch.rand(3, 64, dtype=torch.float64, device="cuda") + 0.1)
+    # one untimed pass at a reduced candidate count: allocator blocks of the set-up buffers, kernel
+    # modules and the collective's buffers are then warm, as they are from the second iteration on
+    wt = model.fused_targets_device(x_fused)
+    wf, wscale, wshift = model.create_fused_GP_batch(x_fused, my_hp, "M52", targets=wt)
+    wres = engine.posterior_sweep(wf, x_test[:4096].contiguous(), wscale, wshift, want_mu=True, want_var=True,
+                                  acq_mask=engine.ACQ_GREEDY, curr_max=float(y_true.max()))
+    wkv, wki, _ = engine.kg_from_sweep(wres)
+    bdist.gather_sets(wkv, wki, n_total=H)
+    del wf, wres
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t_targets, targets = timed(torch, lambda: model.fused_targets_device(x_fused))
     t_setup, (f, scale, shift) = timed(torch, lambda: model.create_fused_GP_batch(x_fused, my_hp, "M52", targets=targets))
     # sets with an ill-conditioned kernel matrix raise in the reference; here they are reported
@@ -86,7 +98,7 @@ def config_reification_kg(args, N, H, tag):
     engine.posterior_events = None
     t_post = sum(x.elapsed_time(y) for x, y in events)
     t_kg, (kv, ki, _) = timed(torch, lambda: engine.kg_from_sweep(res))
-    t_gather, (gv, gi) = timed(torch, lambda: bdist.gather_sets(kv, ki))
+    t_gather, (gv, gi) = timed(torch, lambda: bdist.gather_sets(kv, ki, n_total=H))
     # reification kernel on a large stand-alone batch (HBM roofline)
     P = 10 ** 7
     ym = torch.randn((m, P), dtype=torch.float64, device="cuda")
