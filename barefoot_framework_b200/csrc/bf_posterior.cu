@@ -376,8 +376,11 @@ __global__ void __launch_bounds__(BF_DUAL_THREADS, 1) bf_posterior_dual_kernel(P
 
     const int set = blockIdx.y;
     const int hp = p.set_hp ? p.set_hp[set] : set;
-    const long long t0 = (long long)blockIdx.x * p.tpc;
-    long long t1 = t0 + p.tpc;
+    // balanced split of the tile PAIRS over the CTAs of this set: chunk sizes differ by at most one pair,
+    // so with a CTA count that is a multiple of the SM count every SM gets the same work (no partial wave)
+    const long long npairs_all = (p.ntiles + 1) >> 1;
+    const long long t0 = 2 * (npairs_all * blockIdx.x / p.tiles);
+    long long t1 = 2 * (npairs_all * (blockIdx.x + 1) / p.tiles);
     if (t1 > p.ntiles) t1 = p.ntiles;
     const double amp = p.amp[hp];
     const double* alpha = p.alpha + (size_t)set * p.n;
@@ -614,16 +617,17 @@ static void posterior_chunks(int n, long long N, int S, long long* ntiles, int* 
     *ntiles = nt;
     if (!tc.dual) { *parts = (int)nt; return; }
     const long long sets = S > 0 ? S : 1;
-    long long want = (148LL * 8 + sets - 1) / sets;    // CTAs per set
-    // at least 8 CTAs per set: CTAs that run at the same time then share few sets, so the L^-1 operands
-    // in flight (1 MB per set at n = 500) stay L2-resident instead of streaming from HBM
+    const long long npairs = (nt + 1) / 2;
+    // CTAs per set.  Few sets: 8 CTAs per SM in total (the kernel splits the tile pairs evenly, so every
+    // SM gets the same work and there is no partial last wave).  Many sets: at least 8 CTAs per set, so CTAs that run at the
+    // same time share few sets and the L^-1 operands in flight (1 MB per set at n = 500) stay L2-resident
+    // instead of streaming from HBM.  Never fewer than 4 tile pairs per CTA (prologue amortisation).
+    long long want = (148LL * 8) / sets;               // rounded down: the launch never spills into a ninth wave
     if (want < 8) want = 8;
-    long long per = (nt + want - 1) / want;
-    if (per < 8) per = 8;
-    per += per & 1;            // whole tile pairs
-    if (per > nt) per = nt;
-    *tpc = (int)per;
-    *parts = (int)((nt + per - 1) / per);
+    if (want > (npairs + 3) / 4) want = (npairs + 3) / 4;
+    if (want < 1) want = 1;
+    *tpc = (int)(2 * ((npairs + want - 1) / want));    // upper bound of tiles per CTA (informational)
+    *parts = (int)want;
 }
 
 extern "C" int bf_posterior_parts(int n, long long N, int S) {

@@ -322,3 +322,33 @@ def test_group_best_rejects_keys_out_of_range(pkg):
         engine.group_best(np.array([0, 7, 2]), np.array([1.0, 2.0, 3.0]), 5)
     first, val, row = engine.group_best(np.zeros(0, dtype=np.int64), np.zeros(0), 3)
     assert (first.cpu().numpy() == 0).all() and (row.cpu().numpy() == -1).all()
+
+
+def test_batch_acquisition_multi_host_and_device_candidates_agree(pkg):
+    """The public batch call accepts a device tensor, a pinned host tensor (copied on a side stream while
+    the GP is factorised) or a NumPy array; all three give identical (value, first index) records, also
+    when a maximiser is planted a second time near the end (the earlier index wins,
+    acquisitionFunc.py:135-138)."""
+    from barefoot_framework_b200 import util
+    from barefoot_framework_b200.gpModel import gp_model
+    rng = np.random.default_rng(11)
+    n, d, N = 120, 4, 260000
+    X = np.round(rng.uniform(size=(n, d)), 5)
+    y = np.sum(np.sin(2 * np.pi * X), axis=1)
+    y = (y - y.mean()) / y.std()
+    Xs = np.round(rng.uniform(size=(N, d)), 5)
+    hp = np.column_stack([rng.uniform(0.5, 2.0, size=3), rng.uniform(0.2, 0.9, size=(3, d))])
+    gp = gp_model(X, y, np.ones(d), 1.0, 0.05, d, "M32")
+    dev = util.batch_acquisition_multi(gp, hp, torch.as_tensor(Xs).cuda(), float(y.max()), ("EI", "PI", "UCB"))
+    Xt = Xs.copy()
+    for k, nm in enumerate(("EI", "PI", "UCB")):
+        for h in range(3):
+            Xt[N - 1 - (3 * k + h)] = Xs[int(dev[nm][1][h])]
+    ref = util.batch_acquisition_multi(gp, hp, torch.as_tensor(Xt).cuda(), float(y.max()), ("EI", "PI", "UCB"))
+    host = util.batch_acquisition_multi(gp, hp, torch.as_tensor(Xt).pin_memory(), float(y.max()), ("EI", "PI", "UCB"))
+    plain = util.batch_acquisition_multi(gp, hp, Xt, float(y.max()), ("EI", "PI", "UCB"))
+    for nm in ("EI", "PI", "UCB"):
+        for got in (host, plain):
+            np.testing.assert_array_equal(got[nm][1], ref[nm][1], err_msg=nm)
+            np.testing.assert_array_equal(got[nm][0], ref[nm][0], err_msg=nm)
+        np.testing.assert_array_equal(ref[nm][1], dev[nm][1])    # the planted copies did not win
