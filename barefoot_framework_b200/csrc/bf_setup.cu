@@ -261,7 +261,8 @@ __device__ __forceinline__ void rl_tile_smem(double (&c)[4][4][2], const double*
 }
 
 __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_cholesky_rl_kernel(int n, int np, double* __restrict__ Aall,
-                                                                          int32_t* __restrict__ info) {
+                                                                          int32_t* __restrict__ info,
+                                                                          double* __restrict__ dinv_all) {
     extern __shared__ __align__(16) double rl_sm[];
     double* panel = rl_sm;                                          // (np - 32) x BF_RL_PLD
     double (*Ld)[33] = reinterpret_cast<double (*)[33]>(panel + (size_t)(np - 32) * BF_RL_PLD);
@@ -284,6 +285,11 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_cholesky_rl_kernel(int n,
 #pragma unroll 8
         for (int j = 0; j < 32; ++j) A[(size_t)(r0 + j) * np + r0 + lane] = Ld[j][lane];
         rl_invert_block(Ld, rdiag, Li, lane);
+        if (dinv_all) {                 // inverses of the diagonal blocks, row-major 32 x 32 each (solve path)
+            double* dv = dinv_all + ((size_t)blockIdx.x * (np / 32) + kb) * 1024;
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) dv[j * 32 + lane] = Li[j][lane];     // each lane wrote this column itself
+        }
     };
     if (warp == 0) {
 #pragma unroll 8
@@ -478,13 +484,6 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_factor_finish_rl_kernel(
 #define BF_COLS_RING 8
 #define BF_COLS_TLD 36
 
-__device__ __forceinline__ void bf_cp_async16(void* smem_dst, const void* gsrc) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void bf_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int NKEEP>
-__device__ __forceinline__ void bf_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NKEEP) : "memory"); }
 
 // inverses of the diagonal blocks (warp 0) and zeros right of the diagonal (the other warps): grid (nb, S)
 __global__ void __launch_bounds__(128) bf_diag_inverse_kernel(int np, const double* __restrict__ Lall,
@@ -742,7 +741,22 @@ __global__ void __launch_bounds__(BF_THREADS) bf_cholesky_kernel(int n, int np, 
     if (threadIdx.x == 0 && info) info[blockIdx.x] = bad;
 }
 
+extern "C" int bf_cholesky_dinv_supported(int n) { return bf_padded_n(n) <= BF_SETUP_RL_MAX_NP ? 1 : 0; }
+
+static int cholesky_batched(int n, int S, double* K_inout_L, int32_t* info, double* dinv, void* stream);
+
 extern "C" int bf_cholesky_batched(int n, int S, double* K_inout_L, int32_t* info, void* stream) {
+    return cholesky_batched(n, S, K_inout_L, info, nullptr, stream);
+}
+
+extern "C" int bf_cholesky_batched_dinv(int n, int S, double* K_inout_L, int32_t* info, double* dinv, void* stream) {
+    BF_CHECK_ARG(dinv, BF_ERR_ARG, "bf_cholesky_batched_dinv: null dinv");
+    BF_CHECK_ARG(bf_cholesky_dinv_supported(n), BF_ERR_SIZE, "bf_cholesky_batched_dinv: n=%d too large (padded size above %d)",
+                 n, BF_SETUP_RL_MAX_NP);
+    return cholesky_batched(n, S, K_inout_L, info, dinv, stream);
+}
+
+static int cholesky_batched(int n, int S, double* K_inout_L, int32_t* info, double* dinv, void* stream) {
     BF_CHECK_ARG(n > 0 && S >= 0 && K_inout_L, BF_ERR_ARG, "bf_cholesky_batched: bad argument");
     if (S == 0) return 0;
     const int np = bf_padded_n(n);
@@ -753,7 +767,7 @@ extern "C" int bf_cholesky_batched(int n, int S, double* K_inout_L, int32_t* inf
             bf_set_error("bf_cholesky_batched: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return (int)e;
         }
-        bf_cholesky_rl_kernel<<<S, BF_RL_THREADS, smem, (cudaStream_t)stream>>>(n, np, K_inout_L, info);
+        bf_cholesky_rl_kernel<<<S, BF_RL_THREADS, smem, (cudaStream_t)stream>>>(n, np, K_inout_L, info, dinv);
     } else {
         bf_cholesky_kernel<<<S, BF_THREADS, 0, (cudaStream_t)stream>>>(n, np, K_inout_L, info);
     }

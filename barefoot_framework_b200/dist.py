@@ -87,22 +87,33 @@ def gather_sets(values, indices, n_total=None):
     return (torch.cat([g[:s] for g, s in zip(gv, sizes)]).to(dev), torch.cat([g[:s] for g, s in zip(gi, sizes)]).to(dev))
 
 
+def _gather_packed(*cols):
+    """ONE all-gather of several equally long float64 / int64 vectors (int64 travels bit-cast to float64):
+    returns one [world, len] tensor per input, on the communication device."""
+    r, w = world()
+    n = cols[0].numel()
+    pack = torch.empty((len(cols), n), dtype=torch.float64, device=cols[0].device)
+    for k, c in enumerate(cols):
+        pack[k] = c.view(torch.float64) if c.dtype == torch.int64 else c
+    pack = _comm(pack).view(-1)
+    out = torch.empty((w * len(cols) * n,), dtype=torch.float64, device=pack.device)
+    dist.all_gather_into_tensor(out, pack)
+    out = out.view(w, len(cols), n)
+    return [out[:, k, :].contiguous().view(torch.int64) if c.dtype == torch.int64 else out[:, k, :]
+            for k, c in enumerate(cols)]
+
+
 def reduce_candidate_shards(values, indices, index_offset):
     """Candidate-sharded stages (fewer sets than ranks): every rank holds the per-set maximum over
     ITS candidates, (values [S], local indices [S]).  Returns the maximum over all candidates with
     numpy's first-index tie rule (np.where(v == max)[0][0] over the concatenated candidate array,
-    acquisitionFunc.py:135-138): among equal values the lowest GLOBAL index wins."""
+    acquisitionFunc.py:135-138): among equal values the lowest GLOBAL index wins.  One collective."""
     r, w = world()
     gidx = indices + int(index_offset)
     if w == 1:
         return values, gidx
     dev = values.device
-    values, gidx = _comm(values), _comm(gidx)
-    gv = [torch.empty_like(values) for _ in range(w)]
-    gi = [torch.empty_like(gidx) for _ in range(w)]
-    dist.all_gather(gv, values)
-    dist.all_gather(gi, gidx)
-    gv, gi = torch.stack(gv), torch.stack(gi)            # [world, S]
+    gv, gi = _gather_packed(values.contiguous(), gidx.to(torch.int64).contiguous())      # [world, S] each
     best = gv.max(dim=0).values
     cand = torch.where(gv == best, gi, torch.full_like(gi, _BIG))
     return best.to(dev), cand.min(dim=0).values.to(dev)
@@ -110,20 +121,13 @@ def reduce_candidate_shards(values, indices, index_offset):
 
 def reduce_top2(t1, i1, t2, index_offset):
     """Candidate-sharded KG: combine per-rank (largest mean, its first global index, second largest)
-    into the global triple that bf_kg_diag needs."""
+    into the global triple that bf_kg_diag needs.  One collective."""
     r, w = world()
     gi1 = i1 + int(index_offset)
     if w == 1:
         return t1, gi1, t2
     dev = t1.device
-    t1, gi1, t2 = _comm(t1), _comm(gi1), _comm(t2)
-    a = [torch.empty_like(t1) for _ in range(w)]
-    b = [torch.empty_like(gi1) for _ in range(w)]
-    c = [torch.empty_like(t2) for _ in range(w)]
-    dist.all_gather(a, t1)
-    dist.all_gather(b, gi1)
-    dist.all_gather(c, t2)
-    a, b, c = torch.stack(a), torch.stack(b), torch.stack(c)     # [world, S]
+    a, b, c = _gather_packed(t1.contiguous(), gi1.to(torch.int64).contiguous(), t2.contiguous())   # [world, S]
     best = a.max(dim=0).values
     is_best = a == best
     first = torch.where(is_best, b, torch.full_like(b, _BIG)).min(dim=0).values
