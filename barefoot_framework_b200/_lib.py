@@ -32,6 +32,12 @@ SIGNATURES = {
     "bf_cholesky_batched": (c_i, [c_i, c_i, c_p, c_p, c_p]),
     "bf_factor_finish": (c_i, [c_i, c_i, c_p, c_p, c_ll, c_p, c_p, c_p, c_p]),
     "bf_factor_finish_kernels": (c_i, [c_i, c_i, c_i]),
+    "bf_cholesky_dinv_supported": (c_i, [c_i]),
+    "bf_cholesky_batched_dinv": (c_i, [c_i, c_i, c_p, c_p, c_p, c_p]),
+    "bf_posterior_solve_cols": (c_i, [c_i]),
+    "bf_posterior_solve_parts": (c_i, [c_i, c_ll]),
+    "bf_gp_posterior_solve": (c_i, [c_i, c_ll, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_p,
+                                    c_p, c_p, c_i, c_i, c_d, c_d, c_d, c_p, c_p, c_p]),
     "bf_gp_posterior": (c_i, [c_i, c_ll, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
                               c_p, c_p, c_i, c_i, c_d, c_d, c_d, c_p, c_p, c_p]),
     "bf_gp_solve_rows": (c_i, [c_i, c_ll, c_i, c_i, c_p, c_p, c_p, c_d, c_p, c_p, c_p, c_p, c_p, c_p]),

@@ -146,6 +146,93 @@ def build_factors(kern, X, y, l_sq, sigma_f, yerr, ndim=None, set_hp=None, n_set
                      L=Lbuf if keep_dense else None, Linv=Libuf if keep_dense else None)
 
 
+class SolveSpec:
+    """GPs that are swept over FEW candidates per set (the literal ROM stage, N ~ 50 << n): the inputs of
+    build_factors, kept unfactorised.  posterior_sweep factorises them chunk by chunk and solves
+    L v = [k* | y] directly (bf_gp_posterior_solve) - no L^-1, no alpha, nothing kept per set."""
+
+    def __init__(self, kern, X, y, l_sq, sigma_f, yerr, ndim=None, set_hp=None, chunk_bytes=2 << 30):
+        self.kern = kern
+        self.X = to_dev(X).reshape(len(X), -1)
+        self.n, self.d = self.X.shape
+        self.ndim = self.d if ndim is None else ndim
+        l_sq = np.atleast_2d(np.asarray(l_sq, dtype=np.float64))
+        self.inv_l2 = to_dev(inv_metric(l_sq))
+        self.amp = to_dev(np.atleast_1d(amplitude(sigma_f, self.ndim)))
+        self.set_hp = None if set_hp is None else to_dev(set_hp, torch.int32)
+        self.S = l_sq.shape[0] if set_hp is None else self.set_hp.numel()
+        self.y = to_dev(y)
+        self.y_stride = self.n if self.y.dim() == 2 else 0
+        self.yerr = to_dev(np.atleast_1d(yerr) if not isinstance(yerr, torch.Tensor) else yerr)
+        if self.yerr.dim() == 2:
+            self.yerr_n, self.yerr_stride = self.n, self.n
+        else:
+            self.yerr_n, self.yerr_stride = self.yerr.numel(), 0
+        assert self.yerr_n in (1, self.n)
+        self.chunk_bytes = chunk_bytes
+
+    @staticmethod
+    def supported(n, n_candidates):
+        """The solve path pays off while the candidates of a set are fewer than about half the
+        training points (above that the explicit inverse is amortised)."""
+        cols = _lib.load().bf_posterior_solve_cols(int(n))
+        return cols > 0 and 0 < n_candidates <= max(cols, int(n) // 2)
+
+
+def solve_sweep(f, Xs, scale=None, shift=None, want_mu=False, want_var=False, acq_mask=0,
+                spread_is_sqrt=False, curr_max=0.0, xi=XI, kt=0.0, check=True):
+    """posterior_sweep for a SolveSpec: kernel matrix -> Cholesky (+ diagonal-block inverses) ->
+    forward substitution with the cross-covariances and y as right-hand sides, chunk of sets by chunk."""
+    dev = device()
+    Xs = to_dev(Xs)
+    Xs = Xs.reshape(Xs.shape[0], f.d)
+    N, S, n, d = Xs.shape[0], f.S, f.n, f.d
+    lib = _lib.load()
+    out = SweepResult()
+    if want_mu:
+        out.mu = torch.empty((S, N), dtype=F64, device=dev)
+    if want_var:
+        out.var = torch.empty((S, N), dtype=F64, device=dev)
+    if N == 0:
+        return out
+    if acq_mask:
+        out.best_val = torch.empty((S, NSLOT_VAL), dtype=F64, device=dev)
+        out.best_idx = torch.empty((S, NSLOT_IDX), dtype=torch.int64, device=dev)
+    np_ = lib.bf_padded_n(n)
+    nb = np_ // 32
+    parts = lib.bf_posterior_solve_parts(n, N)
+    per_set = 8 * (np_ * np_ + nb * 1024)
+    chunk = max(1, min(S, 65535, f.chunk_bytes // per_set))
+    Lbuf = torch.empty((chunk, np_, np_), dtype=F64, device=dev)
+    dinv = torch.empty((chunk, nb, 32, 32), dtype=F64, device=dev)
+    info = torch.zeros((S,), dtype=torch.int32, device=dev)
+    pv = pi = None
+    if acq_mask:
+        pv = torch.empty((chunk, parts, NSLOT_VAL), dtype=F64, device=dev)
+        pi = torch.empty((chunk, parts, NSLOT_IDX), dtype=torch.int64, device=dev)
+    st = stream()
+    for s0 in range(0, S, chunk):
+        sc = min(chunk, S - s0)
+        hp_p = None if f.set_hp is None else f.set_hp[s0:].data_ptr()
+        inv_p = f.inv_l2 if f.set_hp is not None else f.inv_l2[s0:]
+        amp_p = f.amp if f.set_hp is not None else f.amp[s0:]
+        call("bf_kernel_matrix", KERN[f.kern], n, d, sc, ptr(f.X), inv_p.data_ptr(), amp_p.data_ptr(), hp_p,
+             f.yerr[s0:].data_ptr() if f.yerr_stride else ptr(f.yerr), f.yerr_n, f.yerr_stride, ptr(Lbuf), st)
+        call("bf_cholesky_batched_dinv", n, sc, ptr(Lbuf), info[s0:].data_ptr(), ptr(dinv), st)
+        call("bf_gp_posterior_solve", KERN[f.kern], N, n, d, sc, ptr(Xs), ptr(f.X), inv_p.data_ptr(), amp_p.data_ptr(),
+             hp_p, ptr(Lbuf), ptr(dinv), f.y[s0:].data_ptr() if f.y_stride else ptr(f.y), f.y_stride,
+             None if scale is None else scale[s0:].data_ptr(), None if shift is None else shift[s0:].data_ptr(),
+             None if out.mu is None else out.mu[s0:].data_ptr(), None if out.var is None else out.var[s0:].data_ptr(),
+             acq_mask, int(bool(spread_is_sqrt)), float(curr_max), float(xi), float(kt), ptr(pv), ptr(pi), st)
+        if acq_mask:
+            call("bf_acq_finalize", sc, parts, acq_mask, ptr(pv), ptr(pi), out.best_val[s0:].data_ptr(),
+                 out.best_idx[s0:].data_ptr(), st)
+    bad = int(info.max().item()) if (S and check) else 0
+    if bad:
+        raise np.linalg.LinAlgError("%d-th leading minor of a GP kernel matrix is not positive definite" % bad)
+    return out
+
+
 class SweepResult:
     def __init__(self):
         self.mu = self.var = self.best_val = self.best_idx = None
@@ -160,6 +247,8 @@ def posterior_sweep(f, Xs, scale=None, shift=None, want_mu=False, want_var=False
     """gp_model.predict_var (gpModel.py:50-54) for every set of `f` at the candidates
     Xs [N, d], with the de-normalisation of predict_fused_GP / predict_low_order
     (reificationFusion.py:189-206) and the elementwise acquisitions fused in."""
+    if isinstance(f, SolveSpec):
+        return solve_sweep(f, Xs, scale, shift, want_mu, want_var, acq_mask, spread_is_sqrt, curr_max, xi, kt)
     dev = device()
     Xs = to_dev(Xs)
     Xs = Xs.reshape(Xs.shape[0], f.d)

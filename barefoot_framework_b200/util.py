@@ -143,13 +143,14 @@ def fused_calculate(param):
 # ---------------------------------------------------------------------------------------------
 def rom_stage_batch(model, x_fused, hp_sets, kernel, x_test, new_mean, acq, cost, curr_max,
                     iteration=1, true_sample_count=None, jj_list=None, kk_list=None, as_arrays=False,
-                    max_bytes_in_flight=16 << 30):
+                    max_bytes_in_flight=16 << 30, solve_path=None):
     """The ROM-stage grid of barefoot.py:1001-1073: for every model jj, fantasy point kk and
     hyper-parameter set mm, update ROM jj with (x_test[kk], new_mean[jj][kk]), rebuild the fused
     GP and evaluate `acq` over x_test.  Returns the rows [max fused mean, value / cost[jj], x*,
     jj, kk, mm] in the reference's loop order (Greedy is not divided by the cost, util.py:876).
     For "Hedge" returns six such row lists in the portfolio order [KG, TS, EI, Greedy, PI, UCB].
     as_arrays=True returns float64 arrays [G * H, 6 (+ 2 d for Greedy)] instead of lists of rows.
+    solve_path: None = automatic (few candidates per fused GP -> engine.SolveSpec, else explicit factors).
 
     The fused targets of one (jj, kk) do not depend on mm; the H fused GPs of every (jj, kk)
     are factorised and swept together (one set per (jj, kk, mm))."""
@@ -169,7 +170,8 @@ def rom_stage_batch(model, x_fused, hp_sets, kernel, x_test, new_mean, acq, cost
     # chunks of at most `max_sets_in_flight` sets so the literal ROM stage of the reference (3 models x 50
     # candidates x 1000 hyper-parameter sets = 150000 fused GPs, 159 GB of factors) fits any budget.
     F = np.asarray(x_fused).shape[0]
-    per_set = 8 * (engine.linv_packed_doubles(F) + 3 * F)
+    use_solve = solve_path if solve_path is not None else engine.SolveSpec.supported(F, N)
+    per_set = 8 * (3 * F + N) if use_solve else 8 * (engine.linv_packed_doubles(F) + 3 * F)
     groups_per_chunk = max(1, int(max_bytes_in_flight // (per_set * H)))
     parts = {nm: ([], []) for nm in names}
     parts["max_mean"] = []
@@ -190,8 +192,12 @@ def rom_stage_batch(model, x_fused, hp_sets, kernel, x_test, new_mean, acq, cost
         scale = ST[:, 1].repeat_interleave(H).contiguous()
         shift = ST[:, 0].repeat_interleave(H).contiguous()
         set_hp = np.tile(np.arange(H, dtype=np.int32), Gc)
-        f = engine.build_factors(kernel, x_fused, Z, hp[:, 1:] ** 2, hp[:, 0], ZE, ndim=model.num_dim,
-                                 set_hp=set_hp)
+        if use_solve:
+            # few candidates per fused GP: factor + forward substitution, no explicit inverse (engine.SolveSpec)
+            f = engine.SolveSpec(kernel, x_fused, Z, hp[:, 1:] ** 2, hp[:, 0], ZE, ndim=model.num_dim, set_hp=set_hp)
+        else:
+            f = engine.build_factors(kernel, x_fused, Z, hp[:, 1:] ** 2, hp[:, 0], ZE, ndim=model.num_dim,
+                                     set_hp=set_hp)
         # calculate_GPHedge hands the variance to PI / UCB (util.py:764-789) and uses x_test.shape[0] for KG
         rc = _sweep(f, scale, shift, x_test, names, "TM" if hedge else "ROM", curr_max, iteration, XI_ROM,
                     M=(N if hedge else M))

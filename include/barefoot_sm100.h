@@ -81,6 +81,12 @@ int bf_kernel_matrix(int kern, int n, int d, int S,
  * non-positive pivot (george would raise LinAlgError). */
 int bf_cholesky_batched(int n, int S, double* K_inout_L, int32_t* info, void* stream);
 
+/* The same factorisation, also storing the inverses of the 32 x 32 diagonal blocks of L:
+ * dinv [S x (np / 32) x 32 x 32] row-major - the operands of the solve path (bf_gp_posterior_solve).
+ * Available when bf_cholesky_dinv_supported(n) (padded size <= 736). */
+int bf_cholesky_dinv_supported(int n);
+int bf_cholesky_batched_dinv(int n, int S, double* K_inout_L, int32_t* info, double* dinv, void* stream);
+
 /* L^-1 (row-major np x np into Linv, and the tensor-core operand layout into linv_packed) and
  * alpha = K^-1 y (george GP._compute_alpha -> cho_solve, reached from gpModel.py:47,53).
  * y is per set (y_stride = n) or shared (y_stride = 0). */
@@ -107,6 +113,24 @@ int bf_gp_posterior(int kern, long long N, int n, int d, int S,
                     double* mu_out, double* var_out,
                     int acq_mask, int spread_is_sqrt, double curr_max, double xi, double kt,
                     double* part_val, long long* part_idx, void* stream);
+
+/* The same posterior for FEW candidates per set (the literal ROM stage: every work item of
+ * barefoot.py:1001-1073 factorises its own fused GP and evaluates only sampleCount ~ 50 candidates,
+ * util.py:243-262).  No L^-1 and no alpha: V = L^-1 [k* | y] by blocked forward substitution,
+ * mu = v_c . t, var = amp - v_c . v_c (t = L^-1 y).  L [S x np x np] and dinv are the outputs of
+ * bf_cholesky_batched_dinv; y [S x n] (y_stride = n) or shared (y_stride = 0).  Outputs and the
+ * partial records as bf_gp_posterior, with parts = bf_posterior_solve_parts(n, N) CTAs per set of
+ * bf_posterior_solve_cols(n) candidates each (0 = n too large for this path). */
+int bf_posterior_solve_cols(int n);
+int bf_posterior_solve_parts(int n, long long N);
+int bf_gp_posterior_solve(int kern, long long N, int n, int d, int S,
+                          const double* Xs, const double* X,
+                          const double* inv_l2, const double* amp, const int32_t* set_hp,
+                          const double* L, const double* dinv, const double* y, long long y_stride,
+                          const double* scale, const double* shift,
+                          double* mu_out, double* var_out,
+                          int acq_mask, int spread_is_sqrt, double curr_max, double xi, double kt,
+                          double* part_val, long long* part_idx, void* stream);
 
 /* Reduce per-tile partials: best_val [S x 5], best_idx [S x 4]; first index wins ties
  * (np.where(v == max)[0][0], acquisitionFunc.py:135-138). */

@@ -107,6 +107,52 @@ def test_inverse_column_groups_agree_with_one_cta_per_set(eng, n, d):
                                    atol=1e-9 * np.abs(many.alpha.cpu().numpy()[h]).max())
 
 
+@pytest.mark.parametrize("kern", ["SE", "M52"])
+@pytest.mark.parametrize("n,d,N", [(5, 1, 1), (33, 2, 7), (70, 3, 31), (200, 6, 32), (500, 6, 50), (500, 6, 100),
+                                   (700, 4, 40), (96, 12, 15)])
+def test_solve_path_matches_oracle_and_the_inverse_path(eng, kern, n, d, N):
+    """bf_gp_posterior_solve (forward substitution, no explicit inverse; the literal ROM stage) against the
+    oracle and against the sweep kernel on the same sets: per-set targets and noise, set -> HP map,
+    de-normalisation, all fused acquisitions."""
+    rng = np.random.default_rng(n * 11 + N)
+    X, _, Xs = make_problem(rng, n, d, max(N, 3))
+    Xs = Xs[:N]
+    H, G = 3, 2
+    S = H * G
+    l = rng.uniform(0.2, 0.9, size=(H, d))
+    sf = rng.uniform(0.5, 3.0, size=H)
+    Y = rng.normal(size=(S, n))
+    YE = rng.uniform(0.03, 0.2, size=(S, n))
+    set_hp = np.tile(np.arange(H, dtype=np.int32), G)
+    scale = eng.to_dev(rng.uniform(0.5, 20.0, size=S))
+    shift = eng.to_dev(rng.normal(size=S))
+    assert eng.SolveSpec.supported(n, N) or N > n // 2
+    spec = eng.SolveSpec(kern, X, Y, l ** 2, sf, YE, set_hp=set_hp)
+    kw = dict(want_mu=True, want_var=True, acq_mask=15, curr_max=0.3, kt=0.5)
+    a = eng.posterior_sweep(spec, Xs, scale, shift, **kw)
+    f = eng.build_factors(kern, X, Y, l ** 2, sf, YE, set_hp=set_hp)
+    b = eng.posterior_sweep(f, Xs, scale, shift, **kw)
+    sc, sh = scale.cpu().numpy(), shift.cpu().numpy()
+    mu, var = a.mu.cpu().numpy(), a.var.cpu().numpy()
+    for s_ in range(S):
+        h = set_hp[s_]
+        g = fast.GP(X, Y[s_], l[h], sf[h], YE[s_], d, kern)
+        mref, vref = g.predict_var(Xs)
+        mref, vref = mref * sc[s_] + sh[s_], vref * sc[s_] ** 2
+        assert np.abs(mu[s_] - mref).max() <= REL * max(1.0, np.abs(mref).max())
+        assert np.abs(var[s_] - vref).max() <= REL * fast.amplitude(sf[h], d) * sc[s_] ** 2
+    assert np.abs(mu - b.mu.cpu().numpy()).max() <= REL * max(1.0, np.abs(mu).max())
+    # selections: equal to the first arg-max of the values this path stored, and to the sweep kernel's
+    # unless two candidates tie to rounding
+    bi = a.best_idx.cpu().numpy()
+    for s_ in range(S):
+        ucb = mu[s_] + 0.5 * var[s_]
+        assert bi[s_, 2] == int(np.where(ucb == ucb.max())[0][0])
+        assert bi[s_, 3] == int(np.where(mu[s_] == mu[s_].max())[0][0])
+    same = bi == b.best_idx.cpu().numpy()
+    assert same.mean() >= 0.9
+
+
 def test_cholesky_reports_non_positive_definite(eng):
     X = np.array([[0.1], [0.1], [0.5]])     # duplicated point, zero noise -> singular
     with pytest.raises(np.linalg.LinAlgError):

@@ -135,8 +135,9 @@ def test_tm_stage_batch(pkg, cidx):
         np.testing.assert_allclose(vals, g[pre + f"tm_{opt}_val"], rtol=1e-8, atol=1e-11, err_msg=opt)
 
 
+@pytest.mark.parametrize("solve_path", [False, True])
 @pytest.mark.parametrize("cidx", [0, 1, 2])
-def test_rom_stage_batch(pkg, cidx):
+def test_rom_stage_batch(pkg, cidx, solve_path):
     g = golden("workitems.npz")
     pre = f"c{cidx}_"
     kern = str(g[pre + "kern"])
@@ -147,7 +148,7 @@ def test_rom_stage_batch(pkg, cidx):
     for opt in ("KG", "EI", "PI", "UCB", "Greedy"):
         rows = pkg.util.rom_stage_batch(model, x_fused, hps, kern, x_test, new_mean, opt, costs,
                                         float(g[pre + "curr_max"]), iteration=3, true_sample_count=x_test.shape[0],
-                                        kk_list=list(g[pre + "rom_kks"]))
+                                        kk_list=list(g[pre + "rom_kks"]), solve_path=solve_path)
         ref = g[pre + f"rom_{opt}"]
         rows = np.array(rows, dtype=np.float64)
         assert rows.shape == ref.shape
