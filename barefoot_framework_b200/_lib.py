@@ -29,6 +29,7 @@ SIGNATURES = {
     "bf_posterior_tile": (c_i, [c_i]),
     "bf_posterior_parts": (c_i, [c_i, c_ll, c_i]),
     "bf_kernel_matrix": (c_i, [c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_p, c_p]),
+    "bf_kernel_matrix_lower": (c_i, [c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_p, c_p]),
     "bf_cholesky_batched": (c_i, [c_i, c_i, c_p, c_p, c_p]),
     "bf_factor_finish": (c_i, [c_i, c_i, c_p, c_p, c_ll, c_p, c_p, c_p, c_p]),
     "bf_factor_finish_kernels": (c_i, [c_i, c_i, c_i]),

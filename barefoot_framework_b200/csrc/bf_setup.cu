@@ -11,7 +11,8 @@
 __global__ void __launch_bounds__(256) bf_kernel_matrix_kernel(
     int kern, int n, int d, int np, const double* __restrict__ X, const double* __restrict__ inv_l2,
     const double* __restrict__ amp, const int32_t* __restrict__ set_hp, const double* __restrict__ yerr,
-    int yerr_n, long long yerr_stride, double* __restrict__ K) {
+    int yerr_n, long long yerr_stride, double* __restrict__ K, int lower_only) {
+    if (lower_only && blockIdx.x > blockIdx.y) return;      // the factorisation never reads the blocks above the diagonal
     __shared__ double xi_s[32][BF_MAX_DIM + 1];
     __shared__ double xj_s[32][BF_MAX_DIM + 1];
     __shared__ double w_s[BF_MAX_DIM];
@@ -53,9 +54,25 @@ __global__ void __launch_bounds__(256) bf_kernel_matrix_kernel(
     }
 }
 
+static int kernel_matrix(int kern, int n, int d, int S, const double* X, const double* inv_l2,
+                         const double* amp, const int32_t* set_hp, const double* yerr,
+                         int yerr_n, long long yerr_stride, double* K, int lower_only, void* stream);
+
 extern "C" int bf_kernel_matrix(int kern, int n, int d, int S, const double* X, const double* inv_l2,
                                 const double* amp, const int32_t* set_hp, const double* yerr,
                                 int yerr_n, long long yerr_stride, double* K, void* stream) {
+    return kernel_matrix(kern, n, d, S, X, inv_l2, amp, set_hp, yerr, yerr_n, yerr_stride, K, 0, stream);
+}
+
+extern "C" int bf_kernel_matrix_lower(int kern, int n, int d, int S, const double* X, const double* inv_l2,
+                                      const double* amp, const int32_t* set_hp, const double* yerr,
+                                      int yerr_n, long long yerr_stride, double* K, void* stream) {
+    return kernel_matrix(kern, n, d, S, X, inv_l2, amp, set_hp, yerr, yerr_n, yerr_stride, K, 1, stream);
+}
+
+static int kernel_matrix(int kern, int n, int d, int S, const double* X, const double* inv_l2,
+                         const double* amp, const int32_t* set_hp, const double* yerr,
+                         int yerr_n, long long yerr_stride, double* K, int lower_only, void* stream) {
     BF_CHECK_ARG(kern >= BF_KERN_SE && kern <= BF_KERN_M52, BF_ERR_ARG, "bf_kernel_matrix: bad kern %d", kern);
     BF_CHECK_ARG(n > 0 && S >= 0 && X && inv_l2 && amp && yerr && K, BF_ERR_ARG, "bf_kernel_matrix: bad argument");
     BF_CHECK_ARG(d >= 1 && d <= BF_MAX_DIM, BF_ERR_SIZE, "bf_kernel_matrix: nDim %d outside 1..%d", d, BF_MAX_DIM);
@@ -65,7 +82,7 @@ extern "C" int bf_kernel_matrix(int kern, int n, int d, int S, const double* X, 
     const int np = bf_padded_n(n);
     dim3 grid(np / 32, np / 32, S);
     bf_kernel_matrix_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(kern, n, d, np, X, inv_l2, amp, set_hp,
-                                                                    yerr, yerr_n, yerr_stride, K);
+                                                                    yerr, yerr_n, yerr_stride, K, lower_only);
     BF_CHECK_LAUNCH("bf_kernel_matrix");
     return 0;
 }

@@ -134,7 +134,7 @@ def build_factors(kern, X, y, l_sq, sigma_f, yerr, ndim=None, set_hp=None, n_set
         inv_p, amp_p = inv_l2, amp
         if hp_t is None:    # identity map: shift the HP rows instead
             inv_p, amp_p = inv_l2[s0:], amp[s0:]
-        call("bf_kernel_matrix", KERN[kern], n, d, sc, ptr(X), inv_p.data_ptr(), amp_p.data_ptr(), hp_p,
+        call("bf_kernel_matrix_lower", KERN[kern], n, d, sc, ptr(X), inv_p.data_ptr(), amp_p.data_ptr(), hp_p,
              yerr_t[s0:].data_ptr() if yerr_stride else ptr(yerr_t), yerr_n, yerr_stride, ptr(Lbuf), st)
         call("bf_cholesky_batched", n, sc, ptr(Lbuf), info[s0:].data_ptr(), st)
         call("bf_factor_finish", n, sc, ptr(Lbuf), y[s0:].data_ptr() if y_stride else ptr(y), y_stride,
@@ -216,7 +216,7 @@ def solve_sweep(f, Xs, scale=None, shift=None, want_mu=False, want_var=False, ac
         hp_p = None if f.set_hp is None else f.set_hp[s0:].data_ptr()
         inv_p = f.inv_l2 if f.set_hp is not None else f.inv_l2[s0:]
         amp_p = f.amp if f.set_hp is not None else f.amp[s0:]
-        call("bf_kernel_matrix", KERN[f.kern], n, d, sc, ptr(f.X), inv_p.data_ptr(), amp_p.data_ptr(), hp_p,
+        call("bf_kernel_matrix_lower", KERN[f.kern], n, d, sc, ptr(f.X), inv_p.data_ptr(), amp_p.data_ptr(), hp_p,
              f.yerr[s0:].data_ptr() if f.yerr_stride else ptr(f.yerr), f.yerr_n, f.yerr_stride, ptr(Lbuf), st)
         call("bf_cholesky_batched_dinv", n, sc, ptr(Lbuf), info[s0:].data_ptr(), ptr(dinv), st)
         call("bf_gp_posterior_solve", KERN[f.kern], N, n, d, sc, ptr(Xs), ptr(f.X), inv_p.data_ptr(), amp_p.data_ptr(),

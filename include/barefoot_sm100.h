@@ -75,6 +75,13 @@ int bf_kernel_matrix(int kern, int n, int d, int S,
                      const int32_t* set_hp,
                      const double* yerr, int yerr_n, long long yerr_stride,
                      double* K, void* stream);
+/* Only the 32 x 32 blocks on and below the diagonal are written (all the factorisation reads; it
+ * clears the blocks above the diagonal itself): half the kernel evaluations and half the writes. */
+int bf_kernel_matrix_lower(int kern, int n, int d, int S,
+                     const double* X, const double* inv_l2, const double* amp,
+                     const int32_t* set_hp,
+                     const double* yerr, int yerr_n, long long yerr_stride,
+                     double* K, void* stream);
 
 /* In-place lower Cholesky of S padded np x np matrices (george BasicSolver.compute ->
  * scipy.linalg.cholesky, reached from gpModel.py:41).  info[s] = 0 or 1 + index of the first

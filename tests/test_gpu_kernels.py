@@ -153,6 +153,27 @@ def test_solve_path_matches_oracle_and_the_inverse_path(eng, kern, n, d, N):
     assert same.mean() >= 0.9
 
 
+def test_kernel_matrix_lower_writes_only_the_blocks_the_factorisation_reads(eng):
+    import torch
+    from barefoot_framework_b200._lib import KERN, call, ptr, stream
+    rng = np.random.default_rng(3)
+    n, d, S = 70, 3, 2
+    X = eng.to_dev(rng.random((n, d)))
+    inv_l2 = eng.to_dev(eng.inv_metric(rng.uniform(0.2, 0.9, size=(S, d)) ** 2))
+    amp = eng.to_dev(np.array([0.4, 1.1]))
+    yerr = eng.to_dev(rng.uniform(0.05, 0.2, size=(S, n)))
+    np_ = 96
+    full = torch.full((S, np_, np_), -7.0, dtype=torch.float64, device=X.device)
+    low = torch.full((S, np_, np_), -7.0, dtype=torch.float64, device=X.device)
+    for name, K in (("bf_kernel_matrix", full), ("bf_kernel_matrix_lower", low)):
+        call(name, KERN["M32"], n, d, S, ptr(X), ptr(inv_l2), ptr(amp), None, ptr(yerr), n, n, ptr(K), stream())
+    full, low = full.cpu().numpy(), low.cpu().numpy()
+    blk = np.arange(np_) // 32
+    lower_blocks = blk[:, None] >= blk[None, :]
+    assert np.array_equal(low[:, lower_blocks], full[:, lower_blocks])
+    assert (low[:, ~lower_blocks] == -7.0).all() and (full != -7.0).all()
+
+
 def test_cholesky_reports_non_positive_definite(eng):
     X = np.array([[0.1], [0.1], [0.5]])     # duplicated point, zero noise -> singular
     with pytest.raises(np.linalg.LinAlgError):

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-kernel timing of the GP set-up path (bf_kernel_matrix, bf_cholesky_batched, bf_factor_finish)
+"""Per-kernel timing of the GP set-up path (bf_kernel_matrix_lower, bf_cholesky_batched, bf_factor_finish)
 for a sweep of (n, S) - the throughput side of SURVEY.md 8f rank 1 (the literal ROM stage factorises
 m * sampleCount * H fused GPs per iteration).
 
@@ -52,7 +52,7 @@ def main():
             for rep in range(args.reps + 1):
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
                 ev[0].record()
-                call("bf_kernel_matrix", KERN[args.kernel], n, d, S, ptr(X), ptr(inv_l2), ptr(amp), None,
+                call("bf_kernel_matrix_lower", KERN[args.kernel], n, d, S, ptr(X), ptr(inv_l2), ptr(amp), None,
                      ptr(yerr), n, n, ptr(K), st)
                 ev[1].record()
                 call("bf_cholesky_batched", n, S, ptr(K), ptr(info), st)
