@@ -82,29 +82,41 @@ class model_reification():
         return gp_error_models
 
     # -- fused GP -------------------------------------------------------------------------------
+    def fused_rows_device(self, x_test, models=None):
+        """reificationFusion.py:143-152 on the device for the given model indices (default: all m): the
+        de-normalised ROM posterior mean and the total variance (discrepancy mean squared + ROM variance,
+        quirk Q5) at x_test.  Returns (means [k, F], variances [k, F]) device tensors."""
+        xs = engine.to_dev(np.asarray(x_test, dtype=np.float64).reshape(len(x_test), -1))
+        F = xs.shape[0]
+        models = list(range(len(self.gp_models))) if models is None else list(models)
+        means = torch.empty((len(models), F), dtype=engine.F64, device=xs.device)
+        variances = torch.empty((len(models), F), dtype=engine.F64, device=xs.device)
+        for row, i in enumerate(models):
+            g = self.gp_models[i]
+            std_i = float(self.model_std[i])
+            r = engine.posterior_sweep(g.gp, xs, want_mu=True, want_var=True)
+            mu = r.mu[0] if not g.mean else r.mu[0] + float(g.mean)
+            means[row] = engine.affine(mu, std_i, float(self.model_mean[i]))
+            e = self.gp_err_models[i]
+            er = engine.posterior_sweep(e.gp, xs, want_mu=True)
+            emu = er.mu[0] if not e.mean else er.mu[0] + float(e.mean)
+            variances[row] = engine.total_variance(emu, float(self.err_std[i]), float(self.err_mean[i]),
+                                                   r.var[0], std_i)
+        return means, variances
+
+    @staticmethod
+    def fused_targets_from_rows(means, variances):
+        """reificationFusion.py:153-159: reification of the m rows, then the z-scored fused targets.
+        Returns (z [F], zerr [F], stats [2] = (mean, std)) as device tensors."""
+        f_mean, f_var = engine.reification(means, variances)
+        return engine.zscore_targets(f_mean, f_var)
+
     def fused_targets_device(self, x_test):
         """reificationFusion.py:143-159 on the device: the 2m posteriors at x_test, the
         de-normalisation, total variance, reification and z-scoring.  Returns
         (z [F], zerr [F], stats [2] = (mean, std)) as device tensors; nothing here depends
         on the fused-GP hyper-parameters, so one call serves every set."""
-        xs = engine.to_dev(np.asarray(x_test, dtype=np.float64).reshape(len(x_test), -1))
-        F = xs.shape[0]
-        m = len(self.gp_models)
-        means = torch.empty((m, F), dtype=engine.F64, device=xs.device)
-        variances = torch.empty((m, F), dtype=engine.F64, device=xs.device)
-        for i in range(m):
-            g = self.gp_models[i]
-            std_i = float(self.model_std[i])
-            r = engine.posterior_sweep(g.gp, xs, want_mu=True, want_var=True)
-            mu = r.mu[0] if not g.mean else r.mu[0] + float(g.mean)
-            means[i] = engine.affine(mu, std_i, float(self.model_mean[i]))
-            e = self.gp_err_models[i]
-            er = engine.posterior_sweep(e.gp, xs, want_mu=True)
-            emu = er.mu[0] if not e.mean else er.mu[0] + float(e.mean)
-            variances[i] = engine.total_variance(emu, float(self.err_std[i]), float(self.err_mean[i]),
-                                                 r.var[0], std_i)
-        f_mean, f_var = engine.reification(means, variances)
-        return engine.zscore_targets(f_mean, f_var)
+        return self.fused_targets_from_rows(*self.fused_rows_device(x_test))
 
     def create_fused_GP(self, x_test, l_param, sigma_f, sigma_n, kernel):
         """reificationFusion.py:137-167.  sigma_n is ignored as in the reference (quirk Q3)."""

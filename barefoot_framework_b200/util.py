@@ -175,13 +175,19 @@ def rom_stage_batch(model, x_fused, hp_sets, kernel, x_test, new_mean, acq, cost
     groups_per_chunk = max(1, int(max_bytes_in_flight // (per_set * H)))
     parts = {nm: ([], []) for nm in names}
     parts["max_mean"] = []
+    base_means, base_vars = model.fused_rows_device(x_fused)
     for g0 in range(0, G, groups_per_chunk):
         chunk = keys[g0:g0 + groups_per_chunk]
         zs, zerrs, stats = [], [], []
         for (jj, kk) in chunk:
             m2 = _fantasy_copy(model, copy)
             m2.update_GP(np.expand_dims(x_test[kk], axis=0), np.expand_dims(np.array([new_mean[jj][kk]]), axis=0), jj)
-            z, zerr, st = m2.fused_targets_device(x_fused)
+            # only ROM jj changed: its row is recomputed, the other rows (and every discrepancy GP) are the
+            # unmodified model's (util.py:243-246 recomputes all 2m posteriors per work item)
+            mj, vj = m2.fused_rows_device(x_fused, models=[jj])
+            means, variances = base_means.clone(), base_vars.clone()
+            means[jj], variances[jj] = mj[0], vj[0]
+            z, zerr, st = m2.fused_targets_from_rows(means, variances)
             zs.append(z)
             zerrs.append(zerr)
             stats.append(st)
