@@ -19,6 +19,13 @@
 
 #include "bf_common.cuh"
 
+// Phase timing (tools/dbg_skip.sh) needs a build with -DBF_PHASE_PROFILE; the shipped library has no such switch.
+#ifdef BF_PHASE_PROFILE
+#define BF_SKIP(p, bit) ((p).debug_skip & (bit))
+#else
+#define BF_SKIP(p, bit) 0
+#endif
+
 struct PostParams {
     int kern, n, d, np, nb, NT, NTA, S;
     long long N;
@@ -33,7 +40,9 @@ struct PostParams {
     int tiles;            // partial slots per set (= CTAs per set)
     int tpc;              // tiles per CTA
     long long ntiles;     // candidate tiles per set
-    int debug_skip;       // profiling only (BF_DEBUG_SKIP): 1 = no phase B, 2 = no phase A, 4 = no phase C
+#ifdef BF_PHASE_PROFILE
+    int debug_skip;       // phase timing builds only: 1 = no phase B, 2 = no phase A, 4 = no phase C (results are wrong)
+#endif
 };
 
 // ---- phase A ------------------------------------------------------------------------------
@@ -476,16 +485,16 @@ __global__ void __launch_bounds__(BF_DUAL_THREADS, 1) bf_posterior_dual_kernel(P
         const bool active = tile < t1;
         double* mp_cur = mpart + buf * 2 * BF_WARPS * NT;
         __syncthreads();     // candidates staged; phase B of the previous pair complete (column sums ready)
-        if (gw == 0 && prev_tile >= 0 && !(p.debug_skip & 4)) finish_tile(prev_tile, mpart + (buf ^ 1) * 2 * BF_WARPS * NT);
-        if (active && !(p.debug_skip & 2)) gen_tile<D, NTA>(p, w_s, xs_s, Bt, mp_cur, alpha, amp, tab_s, g_lo, 1, g_hi, gw);
+        if (gw == 0 && prev_tile >= 0 && !BF_SKIP(p, 4)) finish_tile(prev_tile, mpart + (buf ^ 1) * 2 * BF_WARPS * NT);
+        if (active && !BF_SKIP(p, 2)) gen_tile<D, NTA>(p, w_s, xs_s, Bt, mp_cur, alpha, amp, tab_s, g_lo, 1, g_hi, gw);
         __syncthreads();
         fetch_xs(tile + 2);                                  // in flight during phase B
-        if (active && !(p.debug_skip & 1)) dual_mma<NTA>(p.nb, Aset, Bt, spart, gw);
+        if (active && !BF_SKIP(p, 1)) dual_mma<NTA>(p.nb, Aset, Bt, spart, gw);
         store_xs();
         prev_tile = active ? tile : -1;
     }
     __syncthreads();
-    if (gw == 0 && prev_tile >= 0 && !(p.debug_skip & 4)) finish_tile(prev_tile, mpart + (buf ^ 1) * 2 * BF_WARPS * NT);
+    if (gw == 0 && prev_tile >= 0 && !BF_SKIP(p, 4)) finish_tile(prev_tile, mpart + (buf ^ 1) * 2 * BF_WARPS * NT);
     if (!p.acq_mask) return;
     // the two finishing warps (warp 0 of each group) merge through shared memory
     __shared__ BfBest red_best[3][2];
@@ -701,10 +710,12 @@ extern "C" int bf_gp_posterior(int kern, long long N, int n, int d, int S, const
     p.curr_max = curr_max; p.xi = xi; p.kt = kt;
     p.part_val = part_val; p.part_idx = part_idx;
     posterior_chunks(n, N, S, &p.ntiles, &p.tpc, &p.tiles);
+#ifdef BF_PHASE_PROFILE
     {
-        const char* dbg = getenv("BF_DEBUG_SKIP");   // profiling aid, results are wrong when set
+        const char* dbg = getenv("BF_DEBUG_SKIP");
         p.debug_skip = dbg ? atoi(dbg) : 0;
     }
+#endif
     BF_CHECK_ARG(S <= 65535, BF_ERR_SIZE, "bf_gp_posterior: at most 65535 sets per call (got %d)", S);
     dim3 grid(p.tiles, S);
     cudaStream_t st = (cudaStream_t)stream;

@@ -44,6 +44,13 @@ def main():
     for S in (1, 296):
         l_sq = rng.uniform(0.1, 1.0, size=(S, d)) ** 2
         timed("setup_n500_S%d" % S, lambda: engine.build_factors("M52", X, y, l_sq, np.ones(S), 0.05), S, "sets")
+    # the few-candidates path of the literal ROM stage: 296 fused-GP shaped sets x 50 candidates
+    S = 296
+    spec = engine.SolveSpec("M52", X, rng.standard_normal((S, n)), rng.uniform(0.1, 1.0, size=(S, d)) ** 2, np.ones(S),
+                            rng.uniform(0.02, 0.2, size=(S, n)))
+    xs50 = engine.to_dev(rng.random((50, d)))
+    timed("rom_stage_solve_path_n500_S296_N50", lambda: engine.posterior_sweep(spec, xs50, want_mu=True, want_var=True,
+                                                                               acq_mask=engine.ACQ_GREEDY), S, "sets")
     # knowledge gradient, closed form, on stored mean / variance
     S, N = 64, 10 ** 6
     mu = torch.randn((S, N), dtype=torch.float64, device=dev)
