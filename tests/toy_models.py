@@ -72,6 +72,11 @@ CASES = [
     ("reifi_hedge", dict(reification=True, acquisitionFunc="Hedge", tmSampleOpt="Hedge", initDataPathorNum=[3, 3, 3, 3]),
      dict(covFunc="M52", iterLimit=2, sampleCount=6, hpCount=8, batchSize=2, tmIter=1, fusedPoints=10,
           fusedSamples=60, lowBound=0.05), 4),
+    # a mid-size run: 3 x 30 x 60 = 5400 ROM-stage work items (the few-candidates solve path, chunked),
+    # 60 sets x 500 candidates in the TM stage, k-medoids over the clustered rows
+    ("mid_se_kg", dict(reification=True, acquisitionFunc="KG", tmSampleOpt="KG", initDataPathorNum=[5, 5, 5, 5]),
+     dict(covFunc="SE", iterLimit=2, sampleCount=30, hpCount=60, batchSize=4, tmIter=1, fusedPoints=60,
+          fusedSamples=500, lowBound=0.05), 5),
     ("batch_only_ei", dict(reification=False, acquisitionFunc="EI", tmSampleOpt="EI", initDataPathorNum=[4]),
      dict(covFunc="M32", iterLimit=3, sampleCount=30, hpCount=25, batchSize=3, tmIter=5, fusedPoints=10,
           fusedHP=[3, 0.1, 0.1]), 3),
