@@ -83,6 +83,15 @@ class GPFactors:
         self.linv_packed, self.alpha, self.S = linv_packed, alpha, S
         self.n, self.d = X.shape
         self.L, self.Linv = L, Linv
+        self.info = None
+
+    def raise_if_not_positive_definite(self):
+        """george / SciPy raise LinAlgError from the Cholesky factorisation (gpModel.py:41); here the per-set
+        status of bf_cholesky_batched is read back (one device synchronisation).  build_factors(check=False)
+        lets a caller run the sweep first and call this at the point where it reads its results anyway."""
+        bad = int(self.info.max().item()) if (self.info is not None and self.S) else 0
+        if bad:
+            raise np.linalg.LinAlgError("%d-th leading minor of a GP kernel matrix is not positive definite" % bad)
 
 
 def build_factors(kern, X, y, l_sq, sigma_f, yerr, ndim=None, set_hp=None, n_sets=None,
@@ -139,11 +148,12 @@ def build_factors(kern, X, y, l_sq, sigma_f, yerr, ndim=None, set_hp=None, n_set
         call("bf_cholesky_batched", n, sc, ptr(Lbuf), info[s0:].data_ptr(), st)
         call("bf_factor_finish", n, sc, ptr(Lbuf), y[s0:].data_ptr() if y_stride else ptr(y), y_stride,
              ptr(Libuf), linv_packed[s0:].data_ptr(), alpha[s0:].data_ptr(), st)
-    bad = int(info.max().item()) if (S and check) else 0
-    if bad:
-        raise np.linalg.LinAlgError("%d-th leading minor of a GP kernel matrix is not positive definite" % bad)
-    return GPFactors(kern, X, inv_l2, amp, hp_t, linv_packed, alpha, S,
-                     L=Lbuf if keep_dense else None, Linv=Libuf if keep_dense else None)
+    f = GPFactors(kern, X, inv_l2, amp, hp_t, linv_packed, alpha, S,
+                  L=Lbuf if keep_dense else None, Linv=Libuf if keep_dense else None)
+    f.info = info
+    if check:
+        f.raise_if_not_positive_definite()
+    return f
 
 
 class SolveSpec:

@@ -359,7 +359,9 @@ def batch_acquisition_multi(modelGP, hp_sets, x_test, curr_max, names=("EI", "PI
     x = np.asarray(modelGP.x_train, dtype=np.float64)
     x = x.reshape(x.shape[0], -1)
     y = np.asarray(modelGP.y_train, dtype=np.float64) - float(modelGP.mean)
-    f = engine.build_factors(modelGP.kern, x, y, hp[:, 1:], hp[:, 0], modelGP.sigma_n, ndim=modelGP.n_dim)
+    # the factorisation status is read after the sweep (where the results are read anyway), so the host
+    # does not stall between the set-up and the sweep
+    f = engine.build_factors(modelGP.kern, x, y, hp[:, 1:], hp[:, 0], modelGP.sigma_n, ndim=modelGP.n_dim, check=False)
     if copied is not None:
         torch.cuda.current_stream().wait_event(copied)
         x_test.record_stream(torch.cuda.current_stream())
@@ -372,6 +374,7 @@ def batch_acquisition_multi(modelGP, hp_sets, x_test, curr_max, names=("EI", "PI
     res = engine.posterior_sweep(f, x_test, None if shift is None else torch.ones_like(shift), shift, acq_mask=mask,
                                  spread_is_sqrt=False, curr_max=curr_max, xi=xi,
                                  kt=engine.ucb_kt(f.d, iteration) if "UCB" in names else 0.0)
+    f.raise_if_not_positive_definite()
     if return_device:
         return {nm: (res.best_val[:, _SLOTS[nm]], res.best_idx[:, _SLOTS[nm]]) for nm in names}
     bv, bi = res.best_val.cpu().numpy(), res.best_idx.cpu().numpy()
