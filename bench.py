@@ -21,6 +21,12 @@ import sys
 import threading
 import time
 
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # the reference arm is a CPU run on all host cores; torchrun exports OMP_NUM_THREADS=1 to its workers,
+    # which would pin the BLAS of this arm to one thread if left in place when NumPy / SciPy load
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -81,25 +87,41 @@ def cpu_step(X, y, hp, sn, curr_max, Xs):
     return out
 
 
+_cpu_threads = [1]
+
+
 def cpu_throughput(steps, warmup, sample=CPU_SAMPLE, want_result=False):
+    """The CPU arm uses every host core its BLAS can use, whatever OMP_NUM_THREADS says (torchrun exports
+    OMP_NUM_THREADS=1 to its workers); the thread count actually in force is what `cores` reports."""
     X, y, hp, sn, curr_max, batches = make_workload(0, 1, sample)
-    for _ in range(warmup):
-        cpu_step(X, y, hp, sn, curr_max, batches[0][: max(1000, sample // 10)])
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        out = cpu_step(X, y, hp, sn, curr_max, batches[0])
-    dt = time.perf_counter() - t0
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        limiter = threadpool_limits(limits=os.cpu_count())
+    except Exception:                                   # threadpoolctl missing: whatever the environment gives
+        threadpool_info, limiter = None, None
+    try:
+        if threadpool_info is not None:
+            _cpu_threads[0] = max([int(lib.get("num_threads", 1)) for lib in threadpool_info()] or [1])
+        for _ in range(warmup):
+            cpu_step(X, y, hp, sn, curr_max, batches[0][: max(1000, sample // 10)])
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = cpu_step(X, y, hp, sn, curr_max, batches[0])
+        dt = time.perf_counter() - t0
+    finally:
+        if limiter is not None:
+            limiter.restore_original_limits()
     if want_result:
         return steps * sample / dt, dt / steps, (X, y, hp, sn, curr_max, batches[0], out)
     return steps * sample / dt, dt / steps
 
 
 def cpu_baseline_dict(value, sample, steps):
-    return {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+    return {"value": value, "unit": UNIT, "cores": _cpu_threads[0], "kind": "port",
             "sample": "%d step(s) of %d of the 1e6 candidates (same n, d, kernel, acquisitions); oracle/fast.py "
                       "(NumPy/SciPy float64 restatement of the reference's george path; the reference itself "
-                      "is Python that cannot be imported without george), OpenBLAS threads = all cores"
-                      % (steps, sample)}
+                      "is Python that cannot be imported without george), BLAS threads = %d of %d host cores"
+                      % (steps, sample, _cpu_threads[0], os.cpu_count() or 1)}
 
 
 def run_reference(args):
