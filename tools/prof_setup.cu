@@ -30,7 +30,7 @@ int main() {
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         long long prof[8]; cudaMemcpyFromSymbol(prof, bf_prof_cycles, sizeof(prof));
         int info; cudaMemcpy(&info, dinfo, 4, cudaMemcpyDeviceToHost);
-        printf("rc %d info %d  cholesky %.1f us : diag %lld panel %lld trailing %lld cycles (%s)\n", rc, info, ms * 1e3, prof[0], prof[1],
+        printf("rc %d info %d  cholesky %.1f us : first diagonal block %lld, panels %lld, trailing updates incl. look-ahead diagonal blocks %lld cycles (%s)\n", rc, info, ms * 1e3, prof[0], prof[1],
                prof[2], cudaGetErrorString(cudaGetLastError()));
         cudaMemcpyToSymbol(bf_prof_cycles, zero, sizeof(zero));
         cudaEventRecord(e0);
@@ -38,7 +38,7 @@ int main() {
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         cudaEventElapsedTime(&ms, e0, e1);
         cudaMemcpyFromSymbol(prof, bf_prof_cycles, sizeof(prof));
-        printf("rc %d finish %.1f us : diag-inverses %lld W %lld rows %lld alpha %lld cycles (%s)\n", rc, ms * 1e3, prof[3], prof[4],
+        printf("rc %d finish %.1f us (S = 1 runs the column-group kernels, which carry no phase marks; one-CTA-per-set kernel: diag-inverses %lld W %lld rows %lld alpha %lld cycles) (%s)\n", rc, ms * 1e3, prof[3], prof[4],
                prof[5], prof[6], cudaGetErrorString(cudaGetLastError()));
     }
     return 0;
