@@ -6,7 +6,6 @@
 #include "bf_common.cuh"
 
 #define KM_THREADS 128
-#define KM_TILE 1024
 #define KM_MAX_F 8
 
 __device__ __forceinline__ double km_dist(const double* __restrict__ a, const double* __restrict__ b, int f) {
@@ -18,23 +17,36 @@ __device__ __forceinline__ double km_dist(const double* __restrict__ a, const do
     return sqrt(s);
 }
 
-// rowsum[i - row0] = sum_j |x_i - x_j|: one thread per row, all rows staged tile by tile
-template <int F>
-__global__ void __launch_bounds__(KM_THREADS) bf_km_rowsum_kernel(long long N, const double* __restrict__ X,
-                                                                  long long row0, long long rows,
-                                                                  double* __restrict__ rowsum) {
-    constexpr int TILE = (F <= 4) ? KM_TILE : KM_TILE / 2;
-    __shared__ double tile[TILE * F];
-    const long long r = (long long)blockIdx.x * KM_THREADS + threadIdx.x;
-    const bool live = r < rows;
-    double xi[F];
-#pragma unroll
-    for (int c = 0; c < F; ++c) xi[c] = live ? X[(size_t)(row0 + r) * F + c] : 0.0;
+// ---- sums of distances from a block of 128 "positions" to a run of "members" ----------------------
+// One CTA = 128 positions x KM_GROUPS member groups (1024 threads).  The members are cut into tiles of
+// KM_KT rows; group g takes tiles g, g + 8, ...; every thread keeps four interleaved partial sums over
+// its tiles, and the eight group totals of a position are added in a fixed tree.  The summation order
+// depends only on the member run, never on how rows / chunks are split over launches or ranks, and
+// the eight groups give a latency-bound single-position loop eight times the warps (a rank of an
+// 8-GPU job has only ~100 position blocks per launch).
+#define KM_GROUPS 8
+#define KM_KT 256
+#define KM_BLOCK (KM_THREADS * KM_GROUPS)
+
+template <int F, bool PERM>
+__device__ __forceinline__ double km_block_sum(const double (&xi)[F], long long q0, long long q1,
+                                               const double* __restrict__ X, const long long* __restrict__ perm,
+                                               double* __restrict__ sm) {
+    const int i = threadIdx.x & (KM_THREADS - 1), g = threadIdx.x / KM_THREADS;
+    double* tile = sm + (size_t)g * KM_KT * F;
+    double* part = sm + (size_t)KM_GROUPS * KM_KT * F;             // KM_GROUPS x KM_THREADS
+    const long long ntile = (q1 - q0 + KM_KT - 1) / KM_KT;
+    const long long rounds = (ntile + KM_GROUPS - 1) / KM_GROUPS;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (long long j0 = 0; j0 < N; j0 += TILE) {
-        const int cnt = (int)((N - j0 < TILE) ? (N - j0) : TILE);
+    for (long long rd = 0; rd < rounds; ++rd) {
+        const long long j0 = q0 + (rd * KM_GROUPS + g) * KM_KT;
+        const int cnt = (int)(j0 >= q1 ? 0 : (q1 - j0 < KM_KT ? q1 - j0 : KM_KT));
         __syncthreads();
-        for (int e = threadIdx.x; e < cnt * F; e += KM_THREADS) tile[e] = X[(size_t)j0 * F + e];
+        for (int e = i; e < cnt; e += KM_THREADS) {
+            const long long row = PERM ? perm[j0 + e] : j0 + e;
+#pragma unroll
+            for (int c = 0; c < F; ++c) tile[e * F + c] = X[(size_t)row * F + c];
+        }
         __syncthreads();
         int j = 0;
         for (; j + 4 <= cnt; j += 4) {
@@ -59,7 +71,40 @@ __global__ void __launch_bounds__(KM_THREADS) bf_km_rowsum_kernel(long long N, c
             acc[0] += sqrt(s);
         }
     }
-    if (live) rowsum[r] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    part[g * KM_THREADS + i] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    __syncthreads();
+    return ((part[i] + part[KM_THREADS + i]) + (part[2 * KM_THREADS + i] + part[3 * KM_THREADS + i])) +
+           ((part[4 * KM_THREADS + i] + part[5 * KM_THREADS + i]) + (part[6 * KM_THREADS + i] + part[7 * KM_THREADS + i]));
+}
+
+static size_t km_block_smem(int f) { return sizeof(double) * ((size_t)KM_GROUPS * KM_KT * f + (size_t)KM_GROUPS * KM_THREADS); }
+
+// rowsum[i - row0] = sum_j |x_i - x_j| for rows [row0, row0 + rows) against all N rows
+template <int F>
+__global__ void __launch_bounds__(KM_BLOCK) bf_km_rowsum_kernel(long long N, const double* __restrict__ X,
+                                                                long long row0, long long rows,
+                                                                double* __restrict__ rowsum) {
+    extern __shared__ __align__(16) double km_sm[];
+    const long long r = (long long)blockIdx.x * KM_THREADS + (threadIdx.x & (KM_THREADS - 1));
+    const bool live = r < rows;
+    double xi[F];
+#pragma unroll
+    for (int c = 0; c < F; ++c) xi[c] = live ? X[(size_t)(row0 + r) * F + c] : 0.0;
+    const double total = km_block_sum<F, false>(xi, 0, N, X, nullptr, km_sm);
+    if (live && threadIdx.x < KM_THREADS) rowsum[r] = total;
+}
+
+template <int F>
+static int km_launch_rowsum(long long N, const double* X, long long row0, long long rows, double* rowsum, cudaStream_t st) {
+    const size_t smem = km_block_smem(F);
+    cudaError_t e = cudaFuncSetAttribute(bf_km_rowsum_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        bf_set_error("bf_kmedoids_rowsum: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    const unsigned grid = (unsigned)((rows + KM_THREADS - 1) / KM_THREADS);
+    bf_km_rowsum_kernel<F><<<grid, KM_BLOCK, smem, st>>>(N, X, row0, rows, rowsum);
+    return 0;
 }
 
 extern "C" int bf_kmedoids_rowsum(long long N, int f, const double* X, long long row0, long long rows,
@@ -68,13 +113,14 @@ extern "C" int bf_kmedoids_rowsum(long long N, int f, const double* X, long long
                  "bf_kmedoids_rowsum: bad argument");
     BF_CHECK_ARG(f >= 1 && f <= KM_MAX_F, BF_ERR_SIZE, "bf_kmedoids_rowsum: f=%d outside 1..%d", f, KM_MAX_F);
     if (rows == 0) return 0;
-    const unsigned grid = (unsigned)((rows + KM_THREADS - 1) / KM_THREADS);
     cudaStream_t st = (cudaStream_t)stream;
+    int rc = 0;
     switch (f) {
-#define BF_CASE(FF) case FF: bf_km_rowsum_kernel<FF><<<grid, KM_THREADS, 0, st>>>(N, X, row0, rows, rowsum); break;
+#define BF_CASE(FF) case FF: rc = km_launch_rowsum<FF>(N, X, row0, rows, rowsum, st); break;
         BF_CASE(1) BF_CASE(2) BF_CASE(3) BF_CASE(4) BF_CASE(5) BF_CASE(6) BF_CASE(7) BF_CASE(8)
 #undef BF_CASE
     }
+    if (rc) return rc;
     BF_CHECK_LAUNCH("bf_kmedoids_rowsum");
     return 0;
 }
@@ -206,16 +252,14 @@ extern "C" int bf_kmedoids_sort_labels(long long N, int k, const int32_t* labels
 // ---- in-cluster cost: cost[p] = sum over the segment of p of |x_perm[p] - x_perm[q]|, q in segment order ----
 // Work is cut into chunks of KM_THREADS consecutive positions of ONE cluster, numbered cluster-major;
 // chunk b is computed by the call with b % nparts == part (ranks of a multi-GPU job take one part
-// each; untouched positions keep the caller's zeros so the parts combine by addition).  The members of
-// the cluster are staged through shared memory tile by tile like the row-sum kernel; accumulation
-// order per position: four interleaved partial sums over q - q0 mod 4, remainder into the first.
+// each; untouched positions keep the caller's zeros so the parts combine by addition).  Every chunk is
+// one km_block_sum over the members of its cluster.
 template <int F>
-__global__ void __launch_bounds__(KM_THREADS) bf_km_cost_kernel(int k, const double* __restrict__ X,
-                                                                const long long* __restrict__ perm,
-                                                                const long long* __restrict__ seg, int part, int nparts,
-                                                                double* __restrict__ cost) {
-    constexpr int TILE = (F <= 4) ? KM_TILE : KM_TILE / 2;
-    __shared__ double tile[TILE * F];
+__global__ void __launch_bounds__(KM_BLOCK) bf_km_cost_kernel(int k, const double* __restrict__ X,
+                                                              const long long* __restrict__ perm,
+                                                              const long long* __restrict__ seg, int part, int nparts,
+                                                              double* __restrict__ cost) {
+    extern __shared__ __align__(16) double km_sm[];
     __shared__ long long s_q0, s_q1, s_p0;
     if (threadIdx.x == 0) {
         // chunk index -> (cluster, first position): walk the clusters (k is small)
@@ -237,7 +281,7 @@ __global__ void __launch_bounds__(KM_THREADS) bf_km_cost_kernel(int k, const dou
     __syncthreads();
     const long long q0 = s_q0, q1 = s_q1;
     if (q0 < 0) return;                         // past the last chunk
-    const long long p = s_p0 + threadIdx.x;
+    const long long p = s_p0 + (threadIdx.x & (KM_THREADS - 1));
     const bool live = p < q1;
     double xi[F];
     {
@@ -245,40 +289,21 @@ __global__ void __launch_bounds__(KM_THREADS) bf_km_cost_kernel(int k, const dou
 #pragma unroll
         for (int c = 0; c < F; ++c) xi[c] = live ? X[(size_t)me * F + c] : 0.0;
     }
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (long long j0 = q0; j0 < q1; j0 += TILE) {
-        const int cnt = (int)((q1 - j0 < TILE) ? (q1 - j0) : TILE);
-        __syncthreads();
-        for (int e = threadIdx.x; e < cnt; e += KM_THREADS) {
-            const long long row = perm[j0 + e];
-#pragma unroll
-            for (int c = 0; c < F; ++c) tile[e * F + c] = X[(size_t)row * F + c];
-        }
-        __syncthreads();
-        int j = 0;
-        for (; j + 4 <= cnt; j += 4) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                double s = 0.0;
-#pragma unroll
-                for (int c = 0; c < F; ++c) {
-                    const double d = xi[c] - tile[(j + u) * F + c];
-                    s = fma(d, d, s);
-                }
-                acc[u] += sqrt(s);
-            }
-        }
-        for (; j < cnt; ++j) {
-            double s = 0.0;
-#pragma unroll
-            for (int c = 0; c < F; ++c) {
-                const double d = xi[c] - tile[j * F + c];
-                s = fma(d, d, s);
-            }
-            acc[0] += sqrt(s);
-        }
+    const double total = km_block_sum<F, true>(xi, q0, q1, X, perm, km_sm);
+    if (live && threadIdx.x < KM_THREADS) cost[p] = total;
+}
+
+template <int F>
+static int km_launch_cost(unsigned grid, int k, const double* X, const long long* perm, const long long* seg, int part,
+                          int nparts, double* cost, cudaStream_t st) {
+    const size_t smem = km_block_smem(F);
+    cudaError_t e = cudaFuncSetAttribute(bf_km_cost_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        bf_set_error("bf_kmedoids_cluster_cost: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
     }
-    if (live) cost[p] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    bf_km_cost_kernel<F><<<grid, KM_BLOCK, smem, st>>>(k, X, perm, seg, part, nparts, cost);
+    return 0;
 }
 
 extern "C" int bf_kmedoids_cluster_cost_part(long long N, int f, int k, const double* X, const long long* perm,
@@ -290,11 +315,13 @@ extern "C" int bf_kmedoids_cluster_cost_part(long long N, int f, int k, const do
     const long long max_chunks = (N + KM_THREADS - 1) / KM_THREADS + k;
     const unsigned grid = (unsigned)((max_chunks + nparts - 1) / nparts);
     cudaStream_t st = (cudaStream_t)stream;
+    int rc = 0;
     switch (f) {
-#define BF_CASE(FF) case FF: bf_km_cost_kernel<FF><<<grid, KM_THREADS, 0, st>>>(k, X, perm, seg, part, nparts, cost); break;
+#define BF_CASE(FF) case FF: rc = km_launch_cost<FF>(grid, k, X, perm, seg, part, nparts, cost, st); break;
         BF_CASE(1) BF_CASE(2) BF_CASE(3) BF_CASE(4) BF_CASE(5) BF_CASE(6) BF_CASE(7) BF_CASE(8)
 #undef BF_CASE
     }
+    if (rc) return rc;
     BF_CHECK_LAUNCH("bf_kmedoids_cluster_cost");
     return 0;
 }
