@@ -479,3 +479,85 @@ def test_many_sets_share_training_inputs(eng):
         mref, vref = g.predict_var(Xs)
         assert np.abs(mu[s] - mref).max() <= REL * max(1.0, np.abs(mref).max())
         assert np.abs(var[s] - vref).max() <= REL * sf[h] / d
+
+
+class _Guarded:
+    """Device buffers with sentinel-filled guard bands on both sides (compute-sanitizer is not available on
+    the GPU pool): kernels get the interior view, the bands must come back untouched."""
+
+    def __init__(self, torch):
+        self.torch, self.items = torch, []
+
+    def make(self, numel, dtype, fill=None):
+        t, pad = self.torch, 256
+        sentinel = -12345 if dtype in (t.int32, t.int64, t.uint8) else -1.2345e300
+        if dtype == t.uint8:
+            sentinel = 0xA5
+        full = t.full((numel + 2 * pad,), sentinel, dtype=dtype, device="cuda")
+        view = full[pad:pad + numel]
+        if fill is not None:
+            view.fill_(fill)
+        self.items.append((full, pad, numel, sentinel))
+        return view
+
+    def check(self):
+        for full, pad, numel, sentinel in self.items:
+            assert bool((full[:pad] == sentinel).all()) and bool((full[pad + numel:] == sentinel).all())
+
+
+@pytest.mark.parametrize("n,N", [(70, 9), (500, 50), (333, 31)])
+def test_new_kernels_stay_inside_their_output_buffers(eng, n, N):
+    import torch
+    from barefoot_framework_b200 import _lib
+    from barefoot_framework_b200._lib import KERN, call, ptr, stream
+    lib = _lib.load()
+    rng = np.random.default_rng(n + N)
+    d, S = 3, 3
+    g = _Guarded(torch)
+    X = eng.to_dev(rng.random((n, d)))
+    Xs = eng.to_dev(rng.random((N, d)))
+    inv_l2 = eng.to_dev(eng.inv_metric(rng.uniform(0.2, 0.9, size=(S, d)) ** 2))
+    amp = eng.to_dev(rng.uniform(0.3, 1.0, size=S))
+    yerr = eng.to_dev(np.full(1, 0.05))
+    y = eng.to_dev(rng.normal(size=(S, n)))
+    np_, nb = lib.bf_padded_n(n), lib.bf_padded_n(n) // 32
+    st = stream()
+    # set-up: lower kernel matrix, Cholesky with diagonal-block inverses, column-group inverse + alpha
+    K = g.make(S * np_ * np_, torch.float64)
+    dinv = g.make(S * nb * 1024, torch.float64)
+    info = g.make(S, torch.int32, 0)
+    call("bf_kernel_matrix_lower", KERN["M52"], n, d, S, ptr(X), ptr(inv_l2), ptr(amp), None, ptr(yerr), 1, 0, ptr(K), st)
+    call("bf_cholesky_batched_dinv", n, S, ptr(K), ptr(info), ptr(dinv), st)
+    Linv = g.make(S * np_ * np_, torch.float64)
+    packed = g.make(S * lib.bf_linv_packed_doubles(n), torch.float64)
+    alpha = g.make(S * n, torch.float64)
+    call("bf_factor_finish", n, S, ptr(K), ptr(y), n, ptr(Linv), ptr(packed), ptr(alpha), st)
+    # solve path
+    parts = lib.bf_posterior_solve_parts(n, N)
+    mu, var = g.make(S * N, torch.float64), g.make(S * N, torch.float64)
+    pv, pi = g.make(S * parts * 5, torch.float64), g.make(S * parts * 4, torch.int64)
+    call("bf_gp_posterior_solve", KERN["M52"], N, n, d, S, ptr(Xs), ptr(X), ptr(inv_l2), ptr(amp), None, ptr(K), ptr(dinv),
+         ptr(y), n, None, None, ptr(mu), ptr(var), 15, 0, 0.1, 0.01, 0.5, ptr(pv), ptr(pi), st)
+    bv, bi = g.make(S * 5, torch.float64), g.make(S * 4, torch.int64)
+    call("bf_acq_finalize", S, parts, 15, ptr(pv), ptr(pi), ptr(bv), ptr(bi), st)
+    # k-medoids: label sort, in-cluster cost, row sums
+    Nk, k, f = 10 * n + 7, 5, 3
+    Xk = eng.to_dev(rng.normal(size=(Nk, f)))
+    lab = eng.to_dev(rng.integers(0, k, size=Nk).astype(np.int32), torch.int32)
+    perm, seg = g.make(Nk, torch.int64), g.make(k + 1, torch.int64)
+    ws = g.make(lib.bf_kmedoids_sort_workspace(Nk, k), torch.uint8)
+    cost, rows = g.make(Nk, torch.float64), g.make(Nk - 11, torch.float64)
+    call("bf_kmedoids_sort_labels", Nk, k, ptr(lab), ptr(perm), ptr(seg), ptr(ws), st)
+    call("bf_kmedoids_cluster_cost", Nk, f, k, ptr(Xk), ptr(perm), ptr(seg), ptr(cost), st)
+    call("bf_kmedoids_rowsum", Nk, f, ptr(Xk), 5, Nk - 11, ptr(rows), st)
+    # clustering glue
+    R, G = 777, 41
+    keys = eng.to_dev(rng.integers(0, G, size=R), torch.int64)
+    vals = eng.to_dev(rng.normal(size=R))
+    first, bval, brow = g.make(G, torch.int64), g.make(G, torch.float64), g.make(G, torch.int64)
+    bad = g.make(1, torch.int32, 0)
+    call("bf_group_best", R, G, ptr(keys), ptr(vals), ptr(first), ptr(bval), ptr(brow), ptr(bad), st)
+    torch.cuda.synchronize()
+    g.check()
+    assert int(info.max()) == 0 and int(bad[0]) == 0
+    assert bool(torch.isfinite(mu).all()) and bool(torch.isfinite(var).all()) and bool(torch.isfinite(alpha).all())
