@@ -633,6 +633,22 @@ static void posterior_chunks(int n, long long N, int S, long long* ntiles, int* 
     // instead of streaming from HBM.  Never fewer than 4 tile pairs per CTA (prologue amortisation).
     long long want = (148LL * 8) / sets;               // rounded down: the launch never spills into a ninth wave
     if (want < 8) want = 8;
+    // CTAs take equal time, so a launch of sets * want CTAs costs ceil(sets * want / 148) waves: among up to four
+    // times as many CTAs per set pick the count that wastes the least of its last wave (125 sets per GPU - config #5
+    // on 8 GPUs - would otherwise run 7.6 waves in the time of 8)
+    {
+        long long best = want;
+        double best_eff = 0.0;
+        for (long long w = want; w <= 4 * want; ++w) {
+            const long long ctas = sets * w, waves = (ctas + 147) / 148;
+            const double eff = (double)ctas / (double)(waves * 148);
+            if (eff > best_eff + 1e-3) {
+                best_eff = eff;
+                best = w;
+            }
+        }
+        want = best;
+    }
     if (want > (npairs + 3) / 4) want = (npairs + 3) / 4;
     if (want < 1) want = 1;
     *tpc = (int)(2 * ((npairs + want - 1) / want));    // upper bound of tiles per CTA (informational)
