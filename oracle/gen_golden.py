@@ -221,12 +221,15 @@ def gen_workitems(ref):
     MR = ref["reificationFusion"].model_reification
     out = {}
     cwd = os.getcwd()
-    for cidx, (kern, d) in enumerate((("SE", 2), ("M52", 2), ("M32", 3))):
-        x_train, y_train, x_true, y_true, mp = build_reification_inputs(rng, d=d)
+    # (kernel, nDim, fused points F, candidates N, hyper-parameter sets H, ROM / truth training sizes); the
+    # last case has several 32-row blocks in every factor and six input dimensions
+    cases = (("SE", 2, 24, 36, 6, (9, 11, 8), 6), ("M52", 2, 24, 36, 6, (9, 11, 8), 6),
+             ("M32", 3, 24, 36, 6, (9, 11, 8), 6), ("M52", 6, 70, 50, 5, (40, 45, 38), 20))
+    for cidx, (kern, d, F, N, H, n_rom, n_true) in enumerate(cases):
+        x_train, y_train, x_true, y_true, mp = build_reification_inputs(rng, d=d, n_rom=n_rom, n_true=n_true)
         obj = MR([x.copy() for x in x_train], [y.copy() for y in y_train], mp["model_l"],
                  mp["model_sf"], mp["model_sn"], mp["means"], mp["std"], mp["err_l"],
                  mp["err_sf"], mp["err_sn"], x_true.copy(), y_true.copy(), 3, d, kern)
-        F, N, H = 24, 36, 6
         x_fused = np.round(rng.uniform(size=(F, d)), 5)
         x_test = np.round(rng.uniform(size=(N, d)), 5)
         hps = hp_grid(rng, H, d, low=1e-2)

@@ -113,7 +113,7 @@ def test_reification_function(pkg):
     assert (np.abs(var - g["var_m3"])[ok] <= REL * np.abs(g["var_m3"][ok])).all()
 
 
-@pytest.mark.parametrize("cidx", [0, 1, 2])
+@pytest.mark.parametrize("cidx", [0, 1, 2, 3])
 def test_tm_stage_batch(pkg, cidx):
     g = golden("workitems.npz")
     pre = f"c{cidx}_"
@@ -136,7 +136,7 @@ def test_tm_stage_batch(pkg, cidx):
 
 
 @pytest.mark.parametrize("solve_path", [False, True])
-@pytest.mark.parametrize("cidx", [0, 1, 2])
+@pytest.mark.parametrize("cidx", [0, 1, 2, 3])
 def test_rom_stage_batch(pkg, cidx, solve_path):
     g = golden("workitems.npz")
     pre = f"c{cidx}_"

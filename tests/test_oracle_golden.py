@@ -84,7 +84,7 @@ def _model(g, pre):
         g[pre + "x_true"], g[pre + "y_true"], 3, d, str(g[pre + "kern"]))
 
 
-@pytest.mark.parametrize("cidx", [0, 1, 2])
+@pytest.mark.parametrize("cidx", [0, 1, 2, 3])
 def test_tm_stage_work_items(cidx):
     g = golden("workitems.npz")
     pre = f"c{cidx}_"
@@ -107,7 +107,7 @@ def test_tm_stage_work_items(cidx):
         np.testing.assert_allclose(vals, g[pre + f"tm_{opt}_val"], rtol=1e-9, atol=1e-12)
 
 
-@pytest.mark.parametrize("cidx", [0, 1, 2])
+@pytest.mark.parametrize("cidx", [0, 1, 2, 3])
 def test_rom_stage_work_items(cidx):
     g = golden("workitems.npz")
     pre = f"c{cidx}_"
