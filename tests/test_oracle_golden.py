@@ -177,3 +177,24 @@ def test_cluster_rows_restatement_matches_reference_clustering():
             medoids = [np.where(med_input[:, 0] == np.max(med_input[:, 0]))[0][0]]
         got = rec[[int(med_input[m, 3]) for m in medoids], :]
         np.testing.assert_array_equal(got, want, err_msg=f"case {c}")
+
+
+def test_sampling_and_constraints_match_reference():
+    """barefoot_framework_b200.util.apply_constraints / sampleDesignSpace / composition_sampler / cartesian
+    (host helpers on the caller side of the hot path) reproduce the unmodified reference's outputs on the
+    seeded cases of tests/sampling_cases.py (oracle/gen_sampling.py -> tests/golden/sampling.npz)."""
+    import warnings
+    import sampling_cases
+    from barefoot_framework_b200 import util
+    g = golden("sampling.npz")
+    for name, seed, args, kw in sampling_cases.CASES:
+        np.random.seed(seed)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            x, ok = util.apply_constraints(*args, **kw)
+        np.testing.assert_array_equal(np.asarray(x, dtype=np.float64), g[name + "_x"], err_msg=name)
+        assert bool(ok) == bool(g[name + "_ok"]), name
+    np.random.seed(99)
+    np.testing.assert_array_equal(util.cartesian(np.linspace(0, 1, 3), np.linspace(0, 1, 4), np.array([0.5, 0.7])),
+                                  g["cartesian"])
+    np.testing.assert_array_equal(util.composition_sampler(4, 11), g["composition"])
