@@ -173,3 +173,24 @@ def sum_parts(t):
         return t
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
+
+
+def gather_row_blocks(local, rows_per_rank):
+    """Concatenate 2-D float64 blocks [r_q, C] held by the ranks (r_q = rows_per_rank[q], known to every
+    rank from shard_range) in rank order with ONE all-gather of equally padded blocks.  Used by the ROM
+    stage, whose (model, fantasy point) groups are split over the ranks."""
+    r, w = world()
+    if w == 1:
+        return local
+    assert local.dim() == 2 and local.shape[0] == rows_per_rank[r]
+    dev, C = local.device, local.shape[1]
+    m = max(rows_per_rank)
+    if m == 0:
+        return local
+    pad = torch.zeros((m, C), dtype=torch.float64, device=dev)
+    pad[: local.shape[0]] = local
+    pad = _comm(pad).view(-1)
+    out = torch.empty((w * m * C,), dtype=torch.float64, device=pad.device)
+    dist.all_gather_into_tensor(out, pad)
+    out = out.view(w, m, C)
+    return torch.cat([out[q, : rows_per_rank[q]] for q in range(w)]).to(dev)

@@ -164,7 +164,12 @@ def rom_stage_batch(model, x_fused, hp_sets, kernel, x_test, new_mean, acq, cost
     kk_list = list(range(N)) if kk_list is None else list(kk_list)
     hedge = acq == "Hedge"
     names = _HEDGE_ORDER if hedge else [acq if acq in ("KG", "TS", "EI", "PI", "UCB") else "Greedy"]
-    keys = [(jj, kk) for jj in jj_list for kk in kk_list]
+    all_keys = [(jj, kk) for jj in jj_list for kk in kk_list]
+    # under torchrun the (model, fantasy point) groups are split over the ranks (all H sets of a group stay
+    # local) and the finished rows are gathered in group order; host-RNG members (TS, Hedge) keep one stream
+    sharded = acq not in ("Hedge", "TS") and bdist.world()[1] > 1
+    g_lo, g_hi = bdist.shard_range(len(all_keys)) if sharded else (0, len(all_keys))
+    keys = all_keys[g_lo:g_hi]
     G = len(keys)
     # The factors of one set take ~8 F^2 / 2 bytes (1 MB at F = 500): the (jj, kk) groups are processed in
     # chunks of at most `max_sets_in_flight` sets so the literal ROM stage of the reference (3 models x 50
@@ -212,8 +217,9 @@ def rom_stage_batch(model, x_fused, hp_sets, kernel, x_test, new_mean, acq, cost
             parts[nm][1].append(np.asarray(rc[nm][1], dtype=np.int64))
         parts["max_mean"].append(np.asarray(rc["max_mean"], dtype=np.float64))
         del f, Z, ZE
-    r = {nm: (np.concatenate(parts[nm][0]), np.concatenate(parts[nm][1])) for nm in names}
-    r["max_mean"] = np.concatenate(parts["max_mean"])
+    r = {nm: (np.concatenate(parts[nm][0]) if G else np.zeros(0), np.concatenate(parts[nm][1]) if G else np.zeros(0, dtype=np.int64))
+         for nm in names}
+    r["max_mean"] = np.concatenate(parts["max_mean"]) if G else np.zeros(0)
     # rows [max fused mean, value / cost[jj], x*, jj, kk, mm] for every set, built as arrays (no Python
     # loop over the G * H work items); set s = g * H + mm
     jj_s = np.repeat(np.array([k_[0] for k_ in keys], dtype=np.int64), H)
@@ -232,6 +238,10 @@ def rom_stage_batch(model, x_fused, hp_sets, kernel, x_test, new_mean, acq, cost
             # calculate_Greedy appends the coordinates of the maximum twice (util.py:878-884)
             cols += [x_test[idx], x_test[idx]]
         rows[nm] = np.column_stack(cols)
+        if sharded:
+            w_ = bdist.world()[1]
+            per_rank = [(b_ - a_) * H for a_, b_ in (bdist.shard_range(len(all_keys), q, w_) for q in range(w_))]
+            rows[nm] = bdist.gather_row_blocks(engine.to_dev(np.ascontiguousarray(rows[nm])), per_rank).cpu().numpy()
     if as_arrays:
         return [rows[nm] for nm in names] if hedge else rows[names[0]]
 

@@ -107,6 +107,26 @@ def test_row_blocks_and_cost_parts_combine_exactly():
         np.testing.assert_array_equal(summed, full)
 
 
+def _row_blocks_case(rank, world):
+    from barefoot_framework_b200 import dist as bd
+    G, H, C = 5, 3, 4                                   # 5 groups over 2 ranks: 3 + 2
+    full = np.arange(G * H * C, dtype=np.float64).reshape(G * H, C) * 0.5
+    per_rank = [(b - a) * H for a, b in (bd.shard_range(G, q, world) for q in range(world))]
+    a, b = bd.shard_range(G)
+    got = bd.gather_row_blocks(torch.tensor(full[a * H:b * H]), per_rank)
+    # a rank without any group (1 group over 2 ranks)
+    per1 = [(b_ - a_) * H for a_, b_ in (bd.shard_range(1, q, world) for q in range(world))]
+    a1, b1 = bd.shard_range(1)
+    got1 = bd.gather_row_blocks(torch.tensor(full[a1 * H:b1 * H]), per1)
+    return got.numpy(), got1.numpy(), full, H
+
+
+def test_rom_stage_row_blocks_gather_in_group_order():
+    for got, got1, full, H in _run(_row_blocks_case):
+        np.testing.assert_array_equal(got, full)
+        np.testing.assert_array_equal(got1, full[:H])
+
+
 def test_single_process_is_identity():
     from barefoot_framework_b200 import dist as bd
     v, i = torch.tensor([1.0, 2.0]), torch.tensor([3, 4])
@@ -172,3 +192,37 @@ def test_kmedoids_sharded_over_two_ranks_matches_oracle():
         np.testing.assert_array_equal(l, km.labels_)
         assert it == km.n_iter_
         np.testing.assert_allclose(r, pairwise_euclidean(X).sum(axis=1), rtol=1e-9)
+
+
+def _rom_stage_sharded(rank, world):
+    """Two ranks (gloo; both on cuda:0) split the (model, fantasy point) groups of a ROM-stage call."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    from conftest import golden
+    from barefoot_framework_b200 import reificationFusion, util
+    g = golden("workitems.npz")
+    pre = "c1_"
+    model = reificationFusion.model_reification(
+        [g[pre + f"x_train{i}"].copy() for i in range(3)], [g[pre + f"y_train{i}"].copy() for i in range(3)],
+        g[pre + "model_l"], g[pre + "model_sf"], g[pre + "model_sn"], g[pre + "means"], g[pre + "std"],
+        g[pre + "err_l"], g[pre + "err_sf"], g[pre + "err_sn"], g[pre + "x_true"].copy(), g[pre + "y_true"].copy(),
+        3, int(g[pre + "d"]), str(g[pre + "kern"]))
+    out = {}
+    for opt in ("KG", "EI", "Greedy"):
+        rows = util.rom_stage_batch(model, g[pre + "x_fused"], g[pre + "hps"], str(g[pre + "kern"]), g[pre + "x_test"],
+                                    g[pre + "new_mean"], opt, g[pre + "costs"], float(g[pre + "curr_max"]), iteration=3,
+                                    true_sample_count=g[pre + "x_test"].shape[0], kk_list=list(g[pre + "rom_kks"]),
+                                    as_arrays=True)
+        out[opt] = (np.asarray(rows, dtype=np.float64), g[pre + f"rom_{opt}"])
+    return out
+
+
+@pytest.mark.gpu
+def test_rom_stage_sharded_over_two_ranks_matches_reference():
+    res = _run(_rom_stage_sharded)
+    for out in res:
+        for opt, (rows, ref) in out.items():
+            assert rows.shape == ref.shape, opt
+            np.testing.assert_array_equal(rows[:, 2:], ref[:, 2:], err_msg=opt)         # x*, jj, kk, mm (+ coordinates)
+            np.testing.assert_allclose(rows[:, 0], ref[:, 0], rtol=1e-8, atol=1e-10, err_msg=opt)
+            np.testing.assert_allclose(rows[:, 1], ref[:, 1], rtol=1e-7, atol=1e-10, err_msg=opt)
