@@ -20,6 +20,7 @@ from time import time
 import numpy as np
 import pandas as pd
 
+from . import dist as bdist
 from .gpModel import gp_model
 from .reificationFusion import model_reification
 from .util import (apply_constraints, batch_acquisition_batch, call_model, evaluate_fused_model_batch,
@@ -56,14 +57,26 @@ class barefoot():
                  multiObjective=False, multiObjectRef=[]):
         """Same keywords as the reference constructor (barefoot.py:35-109)."""
         level = logging.DEBUG if verbose else logging.INFO
-        self.logger = logging.getLogger(logname)
+        # Under torchrun every rank runs this orchestrator (the acquisition grids are sharded inside the
+        # batch calls) but the reference has ONE driver process: rank 0 is authoritative.  It alone writes
+        # the log and the result files; its host RNG state is adopted by every rank here, and the wall-clock
+        # model costs that steer the budgets are broadcast from it (_rank0), so that all ranks draw the same
+        # candidates / hyper-parameter sets and take the same branches into the collectives.
+        self.rank, self.world = bdist.world()
+        self.logger = logging.getLogger(logname if self.rank == 0 else "{}.rank{}".format(logname, self.rank))
         for h in list(self.logger.handlers):
             self.logger.removeHandler(h)
         self.logger.setLevel(level)
-        handler = logging.FileHandler('{}.log'.format(logname), mode='w')
-        handler.setLevel(level)
-        handler.setFormatter(logging.Formatter('%(asctime)s - %(name)s - %(levelname)s - %(message)s'))
+        if self.rank == 0:
+            handler = logging.FileHandler('{}.log'.format(logname), mode='w')
+            handler.setLevel(level)
+            handler.setFormatter(logging.Formatter('%(asctime)s - %(name)s - %(levelname)s - %(message)s'))
+        else:
+            handler = logging.NullHandler()
+            self.logger.propagate = False
         self.logger.addHandler(handler)
+        if self.world > 1:
+            np.random.set_state(bdist.broadcast_object(np.random.get_state()))
         self.logger.info("Start BAREFOOT Framework Initialization (B200 path) | Calculation Name: {}".format(
             calculationName))
         if multiObjective:
@@ -124,6 +137,8 @@ class barefoot():
     # files and dataframes (barefoot.py:226-373)
     # ------------------------------------------------------------------------------------------
     def _make_directories(self):
+        if self.rank != 0:
+            return
         for sub in ("results", "data", "data/parameterSets", "results/{}".format(self.calculationName)):
             os.makedirs('{}/{}'.format(self.workingDir, sub), exist_ok=True)
 
@@ -134,7 +149,30 @@ class barefoot():
         self.evaluatedPoints = pd.DataFrame(columns=["Model Index", "Iteration", "y"] + self.inputLabels)
         self.iterationData = pd.DataFrame(columns=iter_cols)
 
+    @staticmethod
+    def _rank0(value):
+        """Rank 0's value of a host quantity that steers the control flow (wall-clock costs)."""
+        return bdist.broadcast_object(value)
+
+    def _model_result(self, job):
+        """call_model (util.py:51-55).  Under torchrun only rank 0 evaluates the user's model (it may be
+        expensive, stateful or not deterministic) and every rank receives its result."""
+        if self.world == 1:
+            return call_model(job)
+        out = None
+        if self.rank == 0:
+            try:
+                out = call_model(job)
+            except Exception as err:                           # noqa: BLE001 - re-raised on every rank
+                out = err
+        out = bdist.broadcast_object(out)
+        if isinstance(out, Exception):
+            raise out
+        return out
+
     def _save_dataframes(self):
+        if self.rank != 0:
+            return
         base = '{}/results/{}'.format(self.workingDir, self.calculationName)
         for name, frame in (("evaluatedPoints", self.evaluatedPoints), ("iterationData", self.iterationData)):
             with open('{}/{}'.format(base, name), 'wb') as f:
@@ -222,7 +260,7 @@ class barefoot():
             filled = [0] * (len(self.ROM) + 1) if self.reification else [0]
             xs, ys, idx = [], [], []
             for job in jobs:
-                results = call_model(job)
+                results = self._model_result(job)
                 if not hasattr(results, "shape"):
                     continue                       # a failed model call returns a non-array and is dropped
                 m = job["Model Index"]
@@ -381,7 +419,7 @@ class barefoot():
         xs, ys, idx, passed = [], [], [], 0
         costs = np.zeros(len(jobs))
         for n, job in enumerate(jobs):
-            results = call_model(job)
+            results = self._model_result(job)
             costs[n] += self.modelCosts[job["Model Index"]]
             if not hasattr(results, "shape"):
                 continue
@@ -517,7 +555,7 @@ class barefoot():
             else:
                 kg_output = out
             medoid_out = self._cluster_rom(kg_output)
-            model_cost = time() - self.timeCheck
+            model_cost = self._rank0(time() - self.timeCheck)
             self.timeCheck = time()
             temp_x, temp_y, temp_index, costs, count, passed = self._call_ROM(
                 medoid_out, x_test[medoid_out[:, 2].astype(int), :])
@@ -599,7 +637,7 @@ class barefoot():
             else:
                 kg_output = np.unique(np.column_stack([out[0], np.asarray(out[1], dtype=np.float64)]), axis=0)
                 medoids = get_medoids(kg_output)
-            model_cost = time() - self.timeCheck
+            model_cost = self._rank0(time() - self.timeCheck)
             self.timeCheck = time()
             jobs = [{"Model Index": -1, "Model": self.TM,
                      "Input Values": np.array(x_test[int(kg_output[m, 1]), :], dtype=float)} for m in medoids]

@@ -17,6 +17,44 @@ def world():
     return 0, 1
 
 
+def broadcast_object(obj, src=0):
+    """Rank `src`'s Python object on every rank (host RNG state, wall-clock costs, stop decisions of the
+    orchestrator): the reference has ONE driver process, so everything that steers the control flow must
+    come from one rank.  Identity in a single process."""
+    r, w = world()
+    if w == 1:
+        return obj
+    box = [obj if r == src else None]
+    if dist.get_backend() == "nccl":
+        dist.broadcast_object_list(box, src=src, device=torch.device("cuda", torch.cuda.current_device()))
+    else:
+        dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+def raise_together(err, what="stage"):
+    """Combine a per-rank failure (None or the exception a rank caught while computing its shard) BEFORE the
+    stage's collective: if any rank failed, every rank raises - the failing ranks their own exception, the
+    others a RuntimeError naming the first failing rank - so no rank is left waiting in an all-gather for a
+    peer that has already unwound (george raises LinAlgError from one work item; the reference's pool then
+    fails the whole map, barefoot.py:1070-1073).  One all-reduce of a single integer."""
+    r, w = world()
+    if w == 1:
+        if err is not None:
+            raise err
+        return
+    flag = torch.tensor([w if err is None else r], dtype=torch.int64)
+    if dist.get_backend() == "nccl":
+        flag = flag.to(torch.device("cuda", torch.cuda.current_device()))
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    first = int(flag.item())
+    if err is not None:
+        raise err
+    if first < w:
+        raise RuntimeError("%s failed on rank %d (see that rank's exception); raised on every rank so that "
+                           "no collective is left half-entered" % (what, first))
+
+
 def gather_host_sets(values, indices, n_total=None):
     """gather_sets for host arrays (numpy in, numpy out); identity in a single process."""
     r, w = world()
@@ -58,7 +96,9 @@ def gather_sets(values, indices, n_total=None):
     dev = values.device
     if n_total is not None:
         sizes = [b - a for a, b in (shard_range(n_total, q, w) for q in range(w))]
-        assert values.numel() == sizes[r], "gather_sets: local block does not match shard_range"
+        if values.numel() != sizes[r] or indices.numel() != sizes[r]:
+            raise ValueError("gather_sets: rank %d holds %d sets, shard_range(%d) gives %d"
+                             % (r, values.numel(), n_total, sizes[r]))
         m = max(sizes)
         pack = torch.zeros((2, m), dtype=torch.float64, device=dev)
         pack[0, : values.numel()] = values
@@ -182,7 +222,9 @@ def gather_row_blocks(local, rows_per_rank):
     r, w = world()
     if w == 1:
         return local
-    assert local.dim() == 2 and local.shape[0] == rows_per_rank[r]
+    if local.dim() != 2 or local.shape[0] != rows_per_rank[r]:
+        raise ValueError("gather_row_blocks: rank %d holds a block of shape %s, expected %d rows"
+                         % (r, tuple(local.shape), rows_per_rank[r]))
     dev, C = local.device, local.shape[1]
     m = max(rows_per_rank)
     if m == 0:

@@ -112,15 +112,23 @@ def fused_calculate_batch(model, x_fused, hp_sets, kernel, x_test, curr_max, sam
     hp = np.atleast_2d(np.asarray(hp_sets, dtype=np.float64))
     deterministic = sampleOpt not in ("Hedge", "TS")          # host RNG draws must stay in one stream
     lo, hi = bdist.shard_range(hp.shape[0]) if deterministic else (0, hp.shape[0])
-    f, scale, shift = model.create_fused_GP_batch(x_fused, hp[lo:hi], kernel, targets=targets)
-    if sampleOpt == "Hedge":
-        r = _sweep(f, scale, shift, x_test, _HEDGE_ORDER, "TM", curr_max, iteration, xi)
-        return [[[r[nm][0][h], int(r[nm][1][h])] for nm in _HEDGE_ORDER] for h in range(f.S)]
     name = sampleOpt if sampleOpt in ("KG", "TS", "EI", "PI", "UCB") else "Greedy"
-    r = _sweep(f, scale, shift, x_test, [name], "TM", curr_max, iteration, xi)
+    err = r = f = None
+    try:
+        f, scale, shift = model.create_fused_GP_batch(x_fused, hp[lo:hi], kernel, targets=targets)
+        r = _sweep(f, scale, shift, x_test, _HEDGE_ORDER if sampleOpt == "Hedge" else [name], "TM", curr_max,
+                   iteration, xi)
+    except Exception as e:                                     # noqa: BLE001 - re-raised on every rank below
+        err = e
     if deterministic:
+        # a set that is not positive definite (or any device error) on ONE rank must fail the stage on all
+        bdist.raise_together(err, "fused_calculate_batch")
         # hyper-parameter sets are sharded over the ranks of a torchrun job; only (value, index) travels
         return bdist.gather_host_sets(*r[name], n_total=hp.shape[0])
+    if err is not None:
+        raise err
+    if sampleOpt == "Hedge":
+        return [[[r[nm][0][h], int(r[nm][1][h])] for nm in _HEDGE_ORDER] for h in range(f.S)]
     return r[name]
 
 
@@ -180,43 +188,51 @@ def rom_stage_batch(model, x_fused, hp_sets, kernel, x_test, new_mean, acq, cost
     groups_per_chunk = max(1, int(max_bytes_in_flight // (per_set * H)))
     parts = {nm: ([], []) for nm in names}
     parts["max_mean"] = []
-    base_means, base_vars = model.fused_rows_device(x_fused)
-    for g0 in range(0, G, groups_per_chunk):
-        chunk = keys[g0:g0 + groups_per_chunk]
-        zs, zerrs, stats = [], [], []
-        for (jj, kk) in chunk:
-            m2 = _fantasy_copy(model, copy)
-            m2.update_GP(np.expand_dims(x_test[kk], axis=0), np.expand_dims(np.array([new_mean[jj][kk]]), axis=0), jj)
-            # only ROM jj changed: its row is recomputed, the other rows (and every discrepancy GP) are the
-            # unmodified model's (util.py:243-246 recomputes all 2m posteriors per work item)
-            mj, vj = m2.fused_rows_device(x_fused, models=[jj])
-            means, variances = base_means.clone(), base_vars.clone()
-            means[jj], variances[jj] = mj[0], vj[0]
-            z, zerr, st = m2.fused_targets_from_rows(means, variances)
-            zs.append(z)
-            zerrs.append(zerr)
-            stats.append(st)
-        Gc = len(chunk)
-        Z = torch.stack(zs).repeat_interleave(H, dim=0).contiguous()          # [Gc*H, F]
-        ZE = torch.stack(zerrs).repeat_interleave(H, dim=0).contiguous()
-        ST = torch.stack(stats)                                               # [Gc, 2] (mean, std)
-        scale = ST[:, 1].repeat_interleave(H).contiguous()
-        shift = ST[:, 0].repeat_interleave(H).contiguous()
-        set_hp = np.tile(np.arange(H, dtype=np.int32), Gc)
-        if use_solve:
-            # few candidates per fused GP: factor + forward substitution, no explicit inverse (engine.SolveSpec)
-            f = engine.SolveSpec(kernel, x_fused, Z, hp[:, 1:] ** 2, hp[:, 0], ZE, ndim=model.num_dim, set_hp=set_hp)
-        else:
-            f = engine.build_factors(kernel, x_fused, Z, hp[:, 1:] ** 2, hp[:, 0], ZE, ndim=model.num_dim,
-                                     set_hp=set_hp)
-        # calculate_GPHedge hands the variance to PI / UCB (util.py:764-789) and uses x_test.shape[0] for KG
-        rc = _sweep(f, scale, shift, x_test, names, "TM" if hedge else "ROM", curr_max, iteration, XI_ROM,
-                    M=(N if hedge else M))
-        for nm in names:
-            parts[nm][0].append(np.asarray(rc[nm][0], dtype=np.float64))
-            parts[nm][1].append(np.asarray(rc[nm][1], dtype=np.int64))
-        parts["max_mean"].append(np.asarray(rc["max_mean"], dtype=np.float64))
-        del f, Z, ZE
+    err = None
+    try:
+        base_means, base_vars = model.fused_rows_device(x_fused)
+        for g0 in range(0, G, groups_per_chunk):
+            chunk = keys[g0:g0 + groups_per_chunk]
+            zs, zerrs, stats = [], [], []
+            for (jj, kk) in chunk:
+                m2 = _fantasy_copy(model, copy)
+                m2.update_GP(np.expand_dims(x_test[kk], axis=0), np.expand_dims(np.array([new_mean[jj][kk]]), axis=0), jj)
+                # only ROM jj changed: its row is recomputed, the other rows (and every discrepancy GP) are the
+                # unmodified model's (util.py:243-246 recomputes all 2m posteriors per work item)
+                mj, vj = m2.fused_rows_device(x_fused, models=[jj])
+                means, variances = base_means.clone(), base_vars.clone()
+                means[jj], variances[jj] = mj[0], vj[0]
+                z, zerr, st = m2.fused_targets_from_rows(means, variances)
+                zs.append(z)
+                zerrs.append(zerr)
+                stats.append(st)
+            Gc = len(chunk)
+            Z = torch.stack(zs).repeat_interleave(H, dim=0).contiguous()          # [Gc*H, F]
+            ZE = torch.stack(zerrs).repeat_interleave(H, dim=0).contiguous()
+            ST = torch.stack(stats)                                               # [Gc, 2] (mean, std)
+            scale = ST[:, 1].repeat_interleave(H).contiguous()
+            shift = ST[:, 0].repeat_interleave(H).contiguous()
+            set_hp = np.tile(np.arange(H, dtype=np.int32), Gc)
+            if use_solve:
+                # few candidates per fused GP: factor + forward substitution, no explicit inverse (engine.SolveSpec)
+                f = engine.SolveSpec(kernel, x_fused, Z, hp[:, 1:] ** 2, hp[:, 0], ZE, ndim=model.num_dim, set_hp=set_hp)
+            else:
+                f = engine.build_factors(kernel, x_fused, Z, hp[:, 1:] ** 2, hp[:, 0], ZE, ndim=model.num_dim,
+                                         set_hp=set_hp)
+            # calculate_GPHedge hands the variance to PI / UCB (util.py:764-789) and uses x_test.shape[0] for KG
+            rc = _sweep(f, scale, shift, x_test, names, "TM" if hedge else "ROM", curr_max, iteration, XI_ROM,
+                        M=(N if hedge else M))
+            for nm in names:
+                parts[nm][0].append(np.asarray(rc[nm][0], dtype=np.float64))
+                parts[nm][1].append(np.asarray(rc[nm][1], dtype=np.int64))
+            parts["max_mean"].append(np.asarray(rc["max_mean"], dtype=np.float64))
+            del f, Z, ZE
+    except Exception as e:                                     # noqa: BLE001 - re-raised below on every rank
+        err = e
+    if sharded:
+        bdist.raise_together(err, "rom_stage_batch")      # before the row gather: all ranks raise or none
+    elif err is not None:
+        raise err
     r = {nm: (np.concatenate(parts[nm][0]) if G else np.zeros(0), np.concatenate(parts[nm][1]) if G else np.zeros(0, dtype=np.int64))
          for nm in names}
     r["max_mean"] = np.concatenate(parts["max_mean"]) if G else np.zeros(0)
@@ -330,30 +346,40 @@ def batch_acquisition_batch(modelGP, hp_sets, x_test, curr_max, acqFunc, iterati
     posterior covariance (util.py:1078-1081) and runs per set through bf_kg_full."""
     x_test = np.asarray(x_test, dtype=np.float64)
     hp = np.atleast_2d(np.asarray(hp_sets, dtype=np.float64))
+    H_total = hp.shape[0]
     if acqFunc not in ("KG", "Hedge", "TS"):
-        lo, hi = bdist.shard_range(hp.shape[0])           # sets sharded over ranks, gathered below
+        lo, hi = bdist.shard_range(H_total)               # sets sharded over ranks, gathered below
         hp = hp[lo:hi]
     x = np.asarray(modelGP.x_train, dtype=np.float64)
     x = x.reshape(x.shape[0], -1)
     y = np.asarray(modelGP.y_train, dtype=np.float64) - float(modelGP.mean)
-    f = engine.build_factors(modelGP.kern, x, y, hp[:, 1:], hp[:, 0], modelGP.sigma_n, ndim=modelGP.n_dim,
-                             keep_dense=acqFunc in ("KG", "Hedge"))
-    shift = None
-    if modelGP.mean:
-        shift = torch.full((f.S,), float(modelGP.mean), dtype=engine.F64, device=f.X.device)
-    scale = None if shift is None else torch.ones_like(shift)
-    if acqFunc in ("KG", "Hedge"):
-        names = [n for n in (_HEDGE_ORDER if acqFunc == "Hedge" else ()) if n != "KG"]
-        r = _sweep(f, scale, shift, x_test, names, "BATCH", curr_max, iteration, xi) if names else {}
-        kv, ki = engine.kg_full_from_factors(f, x_test, shift=float(modelGP.mean), sn=SN_KG)
-        r["KG"] = (kv, ki)
-        if acqFunc == "KG":
-            return r["KG"]
-        return [[[r[nm][0][h], int(r[nm][1][h])] for nm in _HEDGE_ORDER] for h in range(f.S)]
+    sharded = acqFunc not in ("KG", "Hedge", "TS")
     name = acqFunc if acqFunc in ("TS", "EI", "PI", "UCB") else "Greedy"
-    r = _sweep(f, scale, shift, x_test, [name], "BATCH", curr_max, iteration, xi)
-    if name != "TS":
-        return bdist.gather_host_sets(*r[name], n_total=hp.shape[0])
+    err = r = f = None
+    try:
+        f = engine.build_factors(modelGP.kern, x, y, hp[:, 1:], hp[:, 0], modelGP.sigma_n, ndim=modelGP.n_dim,
+                                 keep_dense=acqFunc in ("KG", "Hedge"))
+        shift = None
+        if modelGP.mean:
+            shift = torch.full((f.S,), float(modelGP.mean), dtype=engine.F64, device=f.X.device)
+        scale = None if shift is None else torch.ones_like(shift)
+        if acqFunc in ("KG", "Hedge"):
+            names = [n for n in (_HEDGE_ORDER if acqFunc == "Hedge" else ()) if n != "KG"]
+            r = _sweep(f, scale, shift, x_test, names, "BATCH", curr_max, iteration, xi) if names else {}
+            r["KG"] = engine.kg_full_from_factors(f, x_test, shift=float(modelGP.mean), sn=SN_KG)
+        else:
+            r = _sweep(f, scale, shift, x_test, [name], "BATCH", curr_max, iteration, xi)
+    except Exception as e:                                     # noqa: BLE001 - re-raised on every rank below
+        err = e
+    if sharded:
+        bdist.raise_together(err, "batch_acquisition_batch")   # before the gather: all ranks raise or none
+        return bdist.gather_host_sets(*r[name], n_total=H_total)
+    if err is not None:
+        raise err
+    if acqFunc == "KG":
+        return r["KG"]
+    if acqFunc == "Hedge":
+        return [[[r[nm][0][h], int(r[nm][1][h])] for nm in _HEDGE_ORDER] for h in range(f.S)]
     return r[name]
 
 

@@ -226,3 +226,79 @@ def test_rom_stage_sharded_over_two_ranks_matches_reference():
             np.testing.assert_array_equal(rows[:, 2:], ref[:, 2:], err_msg=opt)         # x*, jj, kk, mm (+ coordinates)
             np.testing.assert_allclose(rows[:, 0], ref[:, 0], rtol=1e-8, atol=1e-10, err_msg=opt)
             np.testing.assert_allclose(rows[:, 1], ref[:, 1], rtol=1e-7, atol=1e-10, err_msg=opt)
+
+
+# ---- failure handling and the orchestrator's single-driver rule ---------------------------------
+def _raise_together_case(rank, world):
+    from barefoot_framework_b200 import dist as bd
+    out = []
+    bd.raise_together(None, "ok stage")                       # nobody failed: returns on every rank
+    out.append("ok")
+    try:
+        bd.raise_together(np.linalg.LinAlgError("bad set") if rank == 1 else None, "stage")
+        out.append("not raised")
+    except np.linalg.LinAlgError:
+        out.append("own")
+    except RuntimeError as e:
+        out.append("peer:" + str(e)[:24])
+    try:                                                      # a block that does not match shard_range
+        bd.gather_sets(torch.zeros(3, dtype=torch.float64), torch.zeros(3, dtype=torch.int64), n_total=100)
+        out.append("not raised")
+    except ValueError:
+        out.append("size")
+    state = bd.broadcast_object({"seed": 17 + rank})
+    out.append(state["seed"])
+    return out
+
+
+def test_failure_on_one_rank_raises_on_every_rank():
+    res = _run(_raise_together_case)
+    assert res[0] == ["ok", "peer:stage failed on rank 1 (", "size", 17]
+    assert res[1] == ["ok", "own", "size", 17]
+
+
+def _batch_only_sharded(rank, world):
+    """batch_acquisition_batch (reification=False path) with H = 7 sets over two ranks (4 + 3): every rank gets
+    all 7 records; a NaN length scale in the last set (rank 1's shard) must raise on BOTH ranks."""
+    from barefoot_framework_b200 import util
+    from barefoot_framework_b200.gpModel import gp_model
+    rng = np.random.default_rng(11)
+    n, d, N, H = 40, 3, 300, 7
+    X = np.round(rng.uniform(size=(n, d)), 5)
+    y = np.sum(np.sin(2 * np.pi * X), axis=1)
+    Xs = np.round(rng.uniform(size=(N, d)), 5)
+    hps = rng.uniform(0.2, 0.8, size=(H, d + 1))
+    gp = gp_model(X, y, np.ones(d), 1, 0.05, d, "M32")
+    out = {}
+    for acq in ("EI", "PI", "UCB", "Greedy"):
+        v, i = util.batch_acquisition_batch(gp, hps, Xs, float(y.max()), acq, iteration=2)
+        out[acq] = (np.asarray(v), np.asarray(i))
+    bad = hps.copy()
+    bad[-1, 1] = np.nan
+    try:
+        util.batch_acquisition_batch(gp, bad, Xs, float(y.max()), "EI", iteration=2)
+        out["bad"] = "not raised"
+    except np.linalg.LinAlgError:
+        out["bad"] = "own"
+    except RuntimeError:
+        out["bad"] = "peer"
+    return out, (X, y, Xs, hps)
+
+
+@pytest.mark.gpu
+def test_batch_only_stage_sharded_over_two_ranks_matches_oracle():
+    from oracle import fast
+    res = _run(_batch_only_sharded)
+    X, y, Xs, hps = res[0][1]
+    d = X.shape[1]
+    for rank, (out, _) in enumerate(res):
+        assert out["bad"] == ("peer" if rank == 0 else "own")
+        for acq in ("EI", "PI", "UCB", "Greedy"):
+            v, i = out[acq]
+            assert v.shape == (hps.shape[0],) and i.shape == (hps.shape[0],)
+            for h in range(hps.shape[0]):
+                g = fast.GP(X, y, hps[h, 1:], hps[h, 0], 0.05, d, "M32", square_l=False)
+                mu, var = g.predict_var(Xs)
+                rv, ri = fast.acquisition(acq, mu, var, float(y.max()), d, 2, "BATCH")
+                assert ri == int(i[h]), (acq, h)
+                assert abs(rv - v[h]) <= 1e-9 * max(1.0, abs(rv)), (acq, h)
