@@ -59,6 +59,11 @@ SIGNATURES = {
     "bf_kmedoids_sort_workspace": (c_sz, [c_ll, c_i]),
     "bf_kmedoids_sort_labels": (c_i, [c_ll, c_i, c_p, c_p, c_p, c_p, c_p]),
     "bf_kmedoids_update": (c_i, [c_ll, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "bf_kmedoids_update_partial": (c_i, [c_ll, c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p]),
+    "bf_kmedoids_update_final": (c_i, [c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "bf_kmedoids_iteration": (c_i, [c_ll, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "bf_probe_dmma_flop": (c_d, [c_i, c_i]),
+    "bf_probe_dmma": (c_i, [c_i, c_i, c_p, c_p]),
     "bf_group_best": (c_i, [c_ll, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "bf_affine": (c_i, [c_ll, c_p, c_d, c_d, c_p, c_p]),
     "bf_total_variance": (c_i, [c_ll, c_p, c_d, c_d, c_p, c_d, c_p, c_p]),
@@ -123,6 +128,8 @@ def call(name, *args):
         launches += lib.bf_factor_finish_kernels(args[0], args[1], 1 if args[7] else 0)
     elif name == "bf_kmedoids_sort_labels":
         launches += 3
+    elif name == "bf_kmedoids_iteration":
+        launches += 6
     elif name == "bf_group_best":
         launches += 4 if args[0] else 2
     else:

@@ -739,8 +739,9 @@ extern "C" int bf_gp_posterior(int kern, long long N, int n, int d, int S, const
     switch (d) {
 #define BF_CASE(DD) case DD: return launch_posterior_tile<DD>(p, tc.dual, grid, smem, st);
         BF_CASE(1) BF_CASE(2) BF_CASE(3) BF_CASE(4) BF_CASE(5) BF_CASE(6) BF_CASE(7) BF_CASE(8)
+        BF_CASE(9) BF_CASE(10) BF_CASE(11) BF_CASE(12) BF_CASE(13) BF_CASE(14) BF_CASE(15) BF_CASE(16)
 #undef BF_CASE
-        default: return launch_posterior_tile<0>(p, tc.dual, grid, smem, st);   // nDim 9..16 at run time
+        default: return launch_posterior_tile<0>(p, tc.dual, grid, smem, st);   // unreachable (nDim <= BF_MAX_DIM); kept as the run-time-dimension form
     }
     return BF_ERR_SIZE;
 }

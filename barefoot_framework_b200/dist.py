@@ -200,6 +200,22 @@ def gather_rows(local, n_total=None):
     return torch.cat([out[q, : b - a] for q, (a, b) in enumerate(sizes)]).to(dev)
 
 
+def all_gather_flat(out, local):
+    """out [world, ...] <- every rank's `local` (equal shapes), one collective; gloo exchanges host copies
+    (CPU tests, ranks sharing one GPU)."""
+    r, w = world()
+    if w == 1:
+        out.copy_(local.reshape(out.shape))
+        return out
+    if dist.get_backend() == "gloo" and local.is_cuda:
+        h = torch.empty(out.shape, dtype=out.dtype)
+        dist.all_gather_into_tensor(h.view(-1), local.cpu().contiguous().view(-1))
+        out.copy_(h)
+        return out
+    dist.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1))
+    return out
+
+
 def sum_parts(t):
     """In-place sum over ranks of a vector whose every element is non-zero on exactly one rank (the
     in-cluster cost parts of k-medoids); adding zeros is exact, so the result is rank-count invariant."""

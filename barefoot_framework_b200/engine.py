@@ -74,6 +74,34 @@ def linv_packed_doubles(n):
     return int(_lib.load().bf_linv_packed_doubles(int(n)))
 
 
+# Measurement hook (bench.py, tools/): set `timeline` to a list and every section below appends
+# (name, start event, end event) recorded on the current stream; None = no events, no overhead.
+timeline = None
+
+
+class _Section:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if timeline is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if timeline is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            timeline.append((self.name, self.e0, e1))
+        return False
+
+
+def section_ms(name):
+    """Sum of the recorded sections called `name` (synchronise first)."""
+    return sum(a.elapsed_time(b) for nm, a, b in (timeline or []) if nm == name)
+
+
 class GPFactors:
     """Factorised GPs sharing the training inputs X: one "set" per hyper-parameter
     set (and, in the ROM stage, per fantasy point)."""
@@ -137,17 +165,18 @@ def build_factors(kern, X, y, l_sq, sigma_f, yerr, ndim=None, set_hp=None, n_set
     Lbuf = torch.empty((chunk, np_, np_), dtype=F64, device=dev)
     Libuf = torch.empty((chunk, np_, np_), dtype=F64, device=dev)
     st = stream()
-    for s0 in range(0, S, chunk):
-        sc = min(chunk, S - s0)
-        hp_p = None if hp_t is None else hp_t[s0:].data_ptr()
-        inv_p, amp_p = inv_l2, amp
-        if hp_t is None:    # identity map: shift the HP rows instead
-            inv_p, amp_p = inv_l2[s0:], amp[s0:]
-        call("bf_kernel_matrix_lower", KERN[kern], n, d, sc, ptr(X), inv_p.data_ptr(), amp_p.data_ptr(), hp_p,
-             yerr_t[s0:].data_ptr() if yerr_stride else ptr(yerr_t), yerr_n, yerr_stride, ptr(Lbuf), st)
-        call("bf_cholesky_batched", n, sc, ptr(Lbuf), info[s0:].data_ptr(), st)
-        call("bf_factor_finish", n, sc, ptr(Lbuf), y[s0:].data_ptr() if y_stride else ptr(y), y_stride,
-             ptr(Libuf), linv_packed[s0:].data_ptr(), alpha[s0:].data_ptr(), st)
+    with _Section("setup"):
+        for s0 in range(0, S, chunk):
+            sc = min(chunk, S - s0)
+            hp_p = None if hp_t is None else hp_t[s0:].data_ptr()
+            inv_p, amp_p = inv_l2, amp
+            if hp_t is None:    # identity map: shift the HP rows instead
+                inv_p, amp_p = inv_l2[s0:], amp[s0:]
+            call("bf_kernel_matrix_lower", KERN[kern], n, d, sc, ptr(X), inv_p.data_ptr(), amp_p.data_ptr(), hp_p,
+                 yerr_t[s0:].data_ptr() if yerr_stride else ptr(yerr_t), yerr_n, yerr_stride, ptr(Lbuf), st)
+            call("bf_cholesky_batched", n, sc, ptr(Lbuf), info[s0:].data_ptr(), st)
+            call("bf_factor_finish", n, sc, ptr(Lbuf), y[s0:].data_ptr() if y_stride else ptr(y), y_stride,
+                 ptr(Libuf), linv_packed[s0:].data_ptr(), alpha[s0:].data_ptr(), st)
     f = GPFactors(kern, X, inv_l2, amp, hp_t, linv_packed, alpha, S,
                   L=Lbuf if keep_dense else None, Linv=Libuf if keep_dense else None)
     f.info = info
@@ -292,14 +321,15 @@ def posterior_sweep(f, Xs, scale=None, shift=None, want_mu=False, want_var=False
         if posterior_events is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        call("bf_gp_posterior", KERN[f.kern], N, f.n, f.d, sc, ptr(Xs), ptr(f.X), inv_p.data_ptr(),
-             amp_p.data_ptr(), hp_p, f.linv_packed[s0:].data_ptr(), f.alpha[s0:].data_ptr(),
-             None if scale is None else scale[s0:].data_ptr(),
-             None if shift is None else shift[s0:].data_ptr(),
-             None if out.mu is None else out.mu[s0:].data_ptr(),
-             None if out.var is None else out.var[s0:].data_ptr(),
-             acq_mask, int(bool(spread_is_sqrt)), float(curr_max), float(xi), float(kt),
-             ptr(pv), ptr(pi), st)
+        with _Section("posterior_kernel"):
+            call("bf_gp_posterior", KERN[f.kern], N, f.n, f.d, sc, ptr(Xs), ptr(f.X), inv_p.data_ptr(),
+                 amp_p.data_ptr(), hp_p, f.linv_packed[s0:].data_ptr(), f.alpha[s0:].data_ptr(),
+                 None if scale is None else scale[s0:].data_ptr(),
+                 None if shift is None else shift[s0:].data_ptr(),
+                 None if out.mu is None else out.mu[s0:].data_ptr(),
+                 None if out.var is None else out.var[s0:].data_ptr(),
+                 acq_mask, int(bool(spread_is_sqrt)), float(curr_max), float(xi), float(kt),
+                 ptr(pv), ptr(pi), st)
         if posterior_events is not None:
             ev1.record()
             posterior_events.append((ev0, ev1))
@@ -390,12 +420,13 @@ def kg_from_sweep(res, M=None, sn=SN_KG, want_nu=False):
     kg_idx = torch.empty((S,), dtype=torch.int64, device=dev)
     nu = torch.full((S, N), float("-inf"), dtype=F64, device=dev) if want_nu else None
     st = stream()
-    for s0 in range(0, S, 65535):
-        sc = min(65535, S - s0)
-        call("bf_kg_diag", N, M, sc, res.mu[s0:].data_ptr(), res.var[s0:].data_ptr(),
-             res.best_val[s0:].data_ptr(), res.best_idx[s0:].data_ptr(), float(sn),
-             None if nu is None else nu[s0:].data_ptr(), pv[s0:].data_ptr(), pi[s0:].data_ptr(),
-             kg_val[s0:].data_ptr(), kg_idx[s0:].data_ptr(), st)
+    with _Section("kg"):
+        for s0 in range(0, S, 65535):
+            sc = min(65535, S - s0)
+            call("bf_kg_diag", N, M, sc, res.mu[s0:].data_ptr(), res.var[s0:].data_ptr(),
+                 res.best_val[s0:].data_ptr(), res.best_idx[s0:].data_ptr(), float(sn),
+                 None if nu is None else nu[s0:].data_ptr(), pv[s0:].data_ptr(), pi[s0:].data_ptr(),
+                 kg_val[s0:].data_ptr(), kg_idx[s0:].data_ptr(), st)
     return kg_val, kg_idx, nu
 
 
@@ -514,8 +545,8 @@ def kmedoids_fit(X, k, max_iter=300, rowsum=None):
     O(N k) work runs on the device: row sums, label assignment, the stable label sort
     (bf_kmedoids_sort_labels), in-cluster costs and the medoid update; the host sees the N row sums
     once (np.argpartition defines the order of the initial medoids) and one `changed` flag per
-    iteration.  Under torchrun the row sums and the in-cluster cost chunks are split over the ranks
-    and combined with one collective each (no other data crosses GPUs)."""
+    iteration.  Under torchrun the row sums and the in-cluster cost chunks are split over the ranks:
+    one all-gather of the row sums, then per iteration one all-gather of k (cost, position) records."""
     from . import dist as bdist
     Xd = to_dev(X)
     N, f = Xd.shape
@@ -537,18 +568,21 @@ def kmedoids_fit(X, k, max_iter=300, rowsum=None):
     # count is the first iteration whose counter is zero (KMedoids.n_iter_)
     changed = torch.zeros((max_iter,), dtype=torch.int32, device=dev)
     st = stream()
-    poll = 4 if N >= 20000 else 1
+    # one host call per iteration (bf_kmedoids_iteration: assign, label sort, this rank's cost chunks, update);
+    # under torchrun each rank reduces its chunks to k (cost, position, current-medoid cost) records, the ranks
+    # all-gather 24 k bytes each and bf_kmedoids_update_final applies the update on every rank
+    recs = gathered = None
+    if world > 1:
+        recs = torch.empty((k, 3), dtype=F64, device=dev)
+        gathered = torch.empty((world, k, 3), dtype=F64, device=dev)
+    poll = (8 if world > 1 else 4) if N >= 20000 else 1
     n_iter = max_iter
     for it in range(max_iter):
-        call("bf_kmedoids_assign", N, f, k, ptr(Xd), ptr(med_d), ptr(labels), st)
-        call("bf_kmedoids_sort_labels", N, k, ptr(labels), ptr(perm), ptr(seg), ptr(ws), st)
+        call("bf_kmedoids_iteration", N, f, k, ptr(Xd), ptr(med_d), ptr(labels), ptr(perm), ptr(seg), ptr(ws),
+             rank, world, ptr(cost), ptr(recs), changed[it:].data_ptr(), st)
         if world > 1:
-            cost.zero_()
-            call("bf_kmedoids_cluster_cost_part", N, f, k, ptr(Xd), ptr(perm), ptr(seg), rank, world, ptr(cost), st)
-            bdist.sum_parts(cost)           # every position is written by exactly one rank: x + 0 = x
-        else:
-            call("bf_kmedoids_cluster_cost", N, f, k, ptr(Xd), ptr(perm), ptr(seg), ptr(cost), st)
-        call("bf_kmedoids_update", N, k, ptr(perm), ptr(seg), ptr(cost), ptr(med_d), changed[it:].data_ptr(), st)
+            bdist.all_gather_flat(gathered, recs)
+            call("bf_kmedoids_update_final", k, world, ptr(gathered), ptr(perm), ptr(med_d), changed[it:].data_ptr(), st)
         if (it + 1) % poll == 0 or it + 1 == max_iter:
             done = (changed[: it + 1] == 0).nonzero()
             if done.numel():

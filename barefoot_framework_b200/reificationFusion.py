@@ -116,7 +116,8 @@ class model_reification():
         de-normalisation, total variance, reification and z-scoring.  Returns
         (z [F], zerr [F], stats [2] = (mean, std)) as device tensors; nothing here depends
         on the fused-GP hyper-parameters, so one call serves every set."""
-        return self.fused_targets_from_rows(*self.fused_rows_device(x_test))
+        with engine._Section("fused_targets"):
+            return self.fused_targets_from_rows(*self.fused_rows_device(x_test))
 
     def create_fused_GP(self, x_test, l_param, sigma_f, sigma_n, kernel):
         """reificationFusion.py:137-167.  sigma_n is ignored as in the reference (quirk Q3)."""

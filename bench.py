@@ -8,11 +8,21 @@ workload config #2: N = 1e6 LHS candidates (rounded to 5 decimals), nDim 6, n = 
 step     one pass of the batch-only work item (util.py:913-1129 of the reference) over one batch of
          candidates: GP setup for the set (kernel matrix, Cholesky, L^-1, alpha) + posterior +
          acquisitions + per-set reduction.  The candidate batches rotate through a ring larger than L2.
-N > 1    weak scaling: every rank sweeps its own batch of N candidates (candidate-tile sharding, SURVEY
-         8e) and the per-rank (value, global index) records are all-gathered over NCCL and reduced
-         with the first-index tie rule.
+N > 1    weak scaling: ONE GP (the same X, y, hyper-parameters on every rank) and 1e6 candidates per rank
+         (candidate-tile sharding): the per-rank (value, global index) records are all-gathered
+         over NCCL and reduced with the first-index tie rule, so `selected` is the arg-max over all N x 1e6
+         candidates.
+configs  next to the headline the same run measures, under the same clock, the other BASELINE configs and
+         prints them as `configs: {"3": .., "4": .., "5": ..}` in the same JSON line:
+           #3  reification of 3 ROMs + discrepancy GPs, KG over 1e5 candidates x 1000 hyper-parameter sets,
+               M52; the sets are sharded over the N ranks (STRONG scaling); 8 sampled sets are compared
+               with oracle/fast.py (index equality, 1e-9 relative values);
+           #4  k-medoids over 1e5 rows (f = 3, k = 10) checked against tests/golden/kmedoids_full.npz, and
+               the posterior kernel at BASELINE #4's stated shape (nDim = 10, M32);
+           #5  (default only at --gpus 8; --configs 2,3,4,5 forces it) 1e6 candidates x 1000 sets + dedupe +
+               kmedoids_max.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--configs 2,3,4]
 """
 import argparse
 import json
@@ -51,14 +61,15 @@ def lhs(rng, n, d):
     return pts
 
 
-def make_workload(seed, n_batches, n_cand=N_CAND):
-    """SURVEY.md 8d config #2."""
-    rng = np.random.default_rng(seed)
+def make_workload(rank, n_batches, n_cand=N_CAND):
+    """SURVEY.md 8d config #2.  The GP (X, y, hyper-parameters) is the SAME on every rank (seed 0); only the
+    candidate batches are per rank, so the cross-rank reduction is the arg-max of one problem."""
+    rng = np.random.default_rng(0)
     X = np.round(lhs(rng, N_TRAIN, N_DIM), 5)
     y = np.sum(np.sin(2 * np.pi * X), axis=1) + 0.05 * rng.normal(size=N_TRAIN)
     y = (y - y.mean()) / y.std()
     hp = np.concatenate(([1.0], rng.uniform(0.05, 1.0, size=N_DIM)))[None]     # [sf, l_1..l_d]
-    batches = [np.round(lhs(np.random.default_rng(seed + 1000 + b), n_cand, N_DIM), 5)
+    batches = [np.round(lhs(np.random.default_rng(1000 + 10 * rank + b), n_cand, N_DIM), 5)
                for b in range(n_batches)]
     return X, y, hp, 0.05, float(y.max()), batches
 
@@ -136,6 +147,7 @@ def run_reference(args):
             "config": config_dict(args.gpus),
             "cpu_baseline": cpu_baseline_dict(value, CPU_SAMPLE, steps),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cpu_baseline_verbatim_reference": verbatim_reference_record(),
             "gpu_launches": 0}
     print(json.dumps(line))
 
@@ -207,6 +219,260 @@ def measure_dgemm_tflops(torch, n=8192, reps=5):
         best = min(best, e0.elapsed_time(e1))
     del a, b, c
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs #3 / #5: reification + fused GP + KG over N candidates x H hyper-parameter sets
+# ---------------------------------------------------------------------------------------------
+def toy(x, shift):
+    return np.sum(np.sin(2 * np.pi * (x + shift)), axis=1) + 0.3 * np.sum(x, axis=1)
+
+
+def hp_grid(rng, H, d, low=1e-4, up=1.0):
+    """initialize_parameters' recipe (barefoot.py:680-692): log-decade linspace grid, independent draws."""
+    top = low * 10
+    grid = np.linspace(low, top, num=H)
+    while top < up:
+        bottom, top = top, min(top * 10, up)
+        grid = np.append(grid, np.linspace(bottom, top, num=H))
+    return grid[rng.integers(0, grid.shape[0], size=(H, d + 1))]
+
+
+def reification_problem(N, H, seed=0):
+    """m = 3 ROM GPs (200 points each) + discrepancy GPs on 50 truth points,
+    d = 6, M52, F = 500 fused points, N LHS candidates, H hyper-parameter sets.  The model outputs are scaled
+    by 100 so that the knowledge gradient (a log, floored at (0, index 0) by the reference,
+    acquisitionFunc.py:56-57) is positive for many candidates and the sets select different points.
+    Identical on every rank (one seed)."""
+    d, m, F = 6, 3, 500
+    rng = np.random.default_rng(seed)
+    x_train = [np.round(lhs(rng, 200, d), 5) for _ in range(m)]
+    y_train = [100.0 * toy(x, sh) for x, sh in zip(x_train, (0.05, 0.12, -0.07))]
+    x_true = np.round(lhs(rng, 50, d), 5)
+    y_true = 100.0 * (toy(x_true, 0.0) + 0.2 * np.sum(x_true ** 2, axis=1))
+    ctor = (x_train, y_train, rng.uniform(0.1, 0.5, size=(m, d)), [1.0] * m, [0.05] * m,
+            [float(np.mean(y)) for y in y_train], [float(np.std(y)) for y in y_train],
+            rng.uniform(0.1, 0.5, size=(m, d)), [1.0] * m, [0.01] * m, x_true, y_true, m, d, "M52")
+    x_fused = np.round(lhs(rng, F, d), 5)
+    x_test = np.round(lhs(rng, N, d), 5)
+    hps = hp_grid(rng, H, d)
+    return {"ctor": ctor, "x_fused": x_fused, "x_test": x_test, "hps": hps, "curr_max": float(y_true.max()),
+            "d": d, "m": m, "F": F}
+
+
+def all_cores():
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        return None
+
+
+def oracle_sets(prob, set_ids):
+    """oracle/fast.py on the sampled hyper-parameter sets: (KG value, index) per set - the checker."""
+    from oracle import fast
+    lim = all_cores()
+    try:
+        c = prob["ctor"]
+        ref = fast.ModelReification([x.copy() for x in c[0]], [y.copy() for y in c[1]], *c[2:])
+        targets = ref.fused_targets(prob["x_fused"])
+        out = []
+        for h in set_ids:
+            hp = prob["hps"][h]
+            ref.create_fused_GP(prob["x_fused"], hp[1:], hp[0], 0.1, "M52", targets=targets)
+            mu, var = ref.predict_fused_GP(prob["x_test"])
+            v, i, _ = fast.kg_diag(mu, var)
+            out.append((float(v), int(i)))
+    finally:
+        if lim is not None:
+            lim.restore_original_limits()
+    return out
+
+
+def run_reification_kg(tag, N, H, peaks, n_check, reps):
+    """One TM-stage-shaped grid through the public call util.fused_calculate_batch (host candidates in,
+    host (value, index) records out; sets sharded over the ranks, one all-gather), then the reference's
+    dedupe (barefoot.py:1290-1300) and kmedoids_max (barefoot.py:1832) on the surviving rows."""
+    import torch
+    import torch.distributed as dist
+    from barefoot_framework_b200 import dist as bdist, engine, util
+    from barefoot_framework_b200.barefoot import barefoot
+    from barefoot_framework_b200.reificationFusion import model_reification
+    rank, world = bdist.world()
+    prob = reification_problem(N, H)
+    c = prob["ctor"]
+    model = model_reification([x.copy() for x in c[0]], [y.copy() for y in c[1]], *c[2:])
+    x_fused, x_test, hps, curr_max = prob["x_fused"], prob["x_test"], prob["hps"], prob["curr_max"]
+    # warm-up at a reduced candidate count: modules, allocator blocks, the collective's buffers
+    util.fused_calculate_batch(model, x_fused, hps, "M52", x_test[:4096], curr_max, "KG")
+    times, post_ms, stage = [], [], {}
+    for _ in range(reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        engine.timeline = []
+        t0 = time.perf_counter()
+        vals, idxs = util.fused_calculate_batch(model, x_fused, hps, "M52", x_test, curr_max, "KG")
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+        tl, engine.timeline = engine.timeline, None
+        per = {}
+        for nm, a, b in tl:
+            per.setdefault(nm, []).append(a.elapsed_time(b))
+        post_ms.append(max(per.get("posterior_kernel", [0.0])))
+        stage = {"fused_targets": sum(per.get("fused_targets", [])), "setup_sets": max(per.get("setup", [0.0])),
+                 "posterior_kernel": post_ms[-1], "kg": sum(per.get("kg", []))}
+    t_pass = min(times)
+    k_ms = post_ms[int(np.argmin(times))]
+    t0 = time.perf_counter()
+    fused_output = barefoot._dedupe(zip(vals, idxs), N)
+    batch = 5
+    picks = util.kmedoids_max(fused_output, batch) if fused_output.shape[0] > batch else np.arange(fused_output.shape[0])
+    torch.cuda.synchronize()
+    t_tail = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_pass, k_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_pass, k_ms = float(t[0]), float(t[1])
+    out = None
+    if rank == 0:
+        a, b = bdist.shard_range(H, 0, world)
+        h_local = b - a                                       # rank 0 holds the largest shard
+        F, d = prob["F"], prob["d"]
+        flop = float(N) * h_local * (F * F + F * (3 * d + 8))
+        achieved = flop / (k_ms * 1e-3) / 1e12
+        chosen = [int(fused_output[p_, 1]) for p_ in picks]
+        set_ids = [int(v) for v in np.linspace(0, H - 1, n_check).round()] if n_check else []
+        chk = oracle_sets(prob, set_ids) if n_check else []
+        idx_ok = all(int(idxs[h]) == ri for h, (rv, ri) in zip(set_ids, chk))
+        rel = max([abs(float(vals[h]) - rv) / max(1.0, abs(rv)) for h, (rv, ri) in zip(set_ids, chk)] or [0.0])
+        # the batch selection against the oracle's kmedoids_max (sklearn distances) on the same rows
+        from oracle import fast
+        ref_picks = fast.kmedoids_max(fused_output, batch)[0] if fused_output.shape[0] > batch else picks
+        out = {"workload": tag, "n_gpus": world, "scaling": "strong (hyper-parameter sets sharded over ranks)",
+               "N": N, "H": H, "F": F, "m": prob["m"], "nDim": d, "kernel": "M52", "acquisition": "KG",
+               "evals_per_s": float(N) * H / t_pass, "s_per_pass": t_pass,
+               "call": "util.fused_calculate_batch (host candidates -> host records)",
+               "h2d_bytes": int(x_test.nbytes), "ms": stage, "tail_ms_dedupe_kmedoids_max": t_tail * 1e3,
+               "roofline": {"bound": "tensor", "kernel": "bf_posterior_dual_kernel<6,3> (M52)", "kernel_ms": k_ms,
+                            "achieved": achieved, "unit": "TFLOP/s", "flop_per_launch": flop,
+                            "frac_of_dgemm": achieved / peaks["dgemm"], "frac_of_dmma_probe": achieved / peaks["dmma"],
+                            "kernel_share_of_pass": k_ms * 1e-3 / t_pass},
+               "selected_first8": [int(v) for v in idxs[:8]], "distinct_selected": int(np.unique(idxs).size),
+               "positive_kg_sets": int(np.sum(np.asarray(vals) > 0)),
+               "rows_after_dedupe": int(fused_output.shape[0]), "batch_selection": chosen,
+               "parity_vs_cpu_oracle": {"sets_checked": set_ids, "indices_match": bool(idx_ok), "max_rel_value_diff": rel,
+                                        "batch_selection_matches": bool(np.array_equal(np.asarray(picks), np.asarray(ref_picks)))}}
+        assert out["distinct_selected"] >= 2, "degenerate workload: every set returned the same index"
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config #4: k-medoids batch selection at N' = 1e5, and the posterior kernel at nDim = 10, M32
+# ---------------------------------------------------------------------------------------------
+def kmedoids_rows(N, f, seed=0):
+    """SURVEY.md 8d config #4 rows (value ~ logN(0,1), candidate index ~ U{0..1e6-1}, model ~ U{0,1,2});
+    the same generator as oracle/gen_kmedoids_full.py, whose golden result is the checker."""
+    rng = np.random.default_rng(seed)
+    cols = [np.exp(rng.normal(size=N)), rng.integers(0, 10 ** 6, size=N).astype(float),
+            rng.integers(0, 3, size=N).astype(float)]
+    return np.ascontiguousarray(np.column_stack(cols[:f]))
+
+
+def run_kmedoids(peaks):
+    import torch
+    import torch.distributed as dist
+    from barefoot_framework_b200 import dist as bdist, engine
+    rank, world = bdist.world()
+    N, f, k = 10 ** 5, 3, 10
+    X = kmedoids_rows(N, f)
+    Xd = engine.to_dev(X)
+    rowsum = (lambda: engine.kmedoids_rowsum_sharded(Xd)) if world > 1 else (lambda: engine.kmedoids_rowsum(Xd))
+    rowsum()
+    engine.kmedoids_fit(Xd[:2000].contiguous(), k)
+
+    def timed(fn):
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms, r
+    t_rowsum, rs = timed(rowsum)
+    t_fit, (med, labels, n_iter) = timed(lambda: engine.kmedoids_fit(Xd, k, rowsum=rs))
+    out = None
+    if rank == 0:
+        gold_path = os.path.join(ROOT, "tests", "golden", "kmedoids_full.npz")
+        parity = None
+        if os.path.isfile(gold_path):
+            g = np.load(gold_path)
+            parity = {"golden": "tests/golden/kmedoids_full.npz (blocked scikit-learn distances, oracle/gen_kmedoids_full.py)",
+                      "medoids_match": bool(np.array_equal(med, g["f3_medoids"])),
+                      "labels_match": bool(np.array_equal(labels, g["f3_labels"].astype(np.int64))),
+                      "n_iter_match": bool(n_iter == int(g["f3_n_iter"]))}
+        sizes = np.bincount(labels, minlength=k).astype(np.float64)
+        out = {"workload": "config #4: k-medoids over 1e5 rows (value, candidate index, model index), k = 10",
+               "n_gpus": world, "N": N, "f": f, "k": k, "iterations": n_iter,
+               "ms": {"rowsum_init": t_rowsum, "alternate_loop": t_fit, "per_iteration": t_fit / n_iter},
+               "rowsum_pairs_per_s": float(N) * N / (t_rowsum * 1e-3),
+               "in_cluster_pairs_final_iteration": float(np.sum(sizes ** 2)),
+               "medoids": [int(v) for v in med], "parity_vs_golden": parity}
+    return out
+
+
+def run_posterior_shape(kern, d, peaks, n=500, N=10 ** 6):
+    """Posterior + EI/PI/UCB at another kernel / nDim (BASELINE #4 states nDim = 10, M32): device-resident
+    candidates, H = 1, CUDA events around the posterior launch.  Rank 0 only."""
+    import torch
+    from barefoot_framework_b200 import engine
+    rng = np.random.default_rng(4)
+    X = np.round(lhs(rng, n, d), 5)
+    y = np.sum(np.sin(2 * np.pi * X), axis=1)
+    y = (y - y.mean()) / y.std()
+    hp = np.concatenate(([1.0], rng.uniform(0.3, 1.0, size=d)))[None]
+    Xs = engine.to_dev(np.round(rng.uniform(size=(N, d)), 5))
+    f = engine.build_factors(kern, X, y, hp[:, 1:], hp[:, 0], 0.05, ndim=d)
+    mask = engine.ACQ_EI | engine.ACQ_PI | engine.ACQ_UCB
+    ms = []
+    for it in range(4):
+        engine.timeline = []
+        engine.posterior_sweep(f, Xs, acq_mask=mask, curr_max=float(y.max()), kt=engine.ucb_kt(d, 1))
+        torch.cuda.synchronize()
+        ms.append(engine.section_ms("posterior_kernel"))
+        engine.timeline = None
+    k_ms = min(ms[1:])
+    flop = float(N) * (n * n + n * (3 * d + 6))
+    achieved = flop / (k_ms * 1e-3) / 1e12
+    return {"kernel": kern, "nDim": d, "n": n, "N": N, "H": 1, "kernel_ms": k_ms, "evals_per_s": N / (k_ms * 1e-3),
+            "achieved_tflops": achieved, "frac_of_dgemm": achieved / peaks["dgemm"],
+            "frac_of_dmma_probe": achieved / peaks["dmma"]}
+
+
+def measure_dmma_probe_tflops(torch, reps=5):
+    """FP64 tensor issue rate: bf_probe_dmma (148 CTAs x 8 warps x 12 independent DMMA chains)."""
+    from barefoot_framework_b200 import _lib
+    lib = _lib.load()
+    ctas, iters = 148, 20000
+    out = torch.empty((ctas * 256,), dtype=torch.float64, device="cuda")
+    _lib.call("bf_probe_dmma", ctas, 200, out.data_ptr(), _lib.stream())
+    torch.cuda.synchronize()
+    best = float("inf")
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call("bf_probe_dmma", ctas, iters, out.data_ptr(), _lib.stream())
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return lib.bf_probe_dmma_flop(ctas, iters) / (best * 1e-3) / 1e12
 
 
 def run_gpu(args):
@@ -301,8 +567,27 @@ def run_gpu(args):
     value = evals / (ms * 1e-3)
     e2e_value = evals / (ms_e2e * 1e-3)
 
+    # ---- roofline denominators (rank 0) and the other BASELINE configs, under the same clock ----
+    peaks = {"dgemm": 1.0, "dmma": 1.0}
     if rank == 0:
-        dgemm = measure_dgemm_tflops(torch)
+        peaks = {"dgemm": measure_dgemm_tflops(torch), "dmma": measure_dmma_probe_tflops(torch)}
+    wanted = set(int(c) for c in args.configs.split(",") if c.strip()) if args.configs else ({2, 3, 4} | ({5} if world == 8 else set()))
+    cfgs = {}
+    if 3 in wanted:
+        cfgs["3"] = run_reification_kg("config #3: reification of 3 ROMs + discrepancy GPs, KG over 1e5 candidates x 1000 "
+                                       "hyper-parameter sets, M52", 10 ** 5, 1000, peaks, n_check=8, reps=2)
+    if 4 in wanted:
+        cfgs["4"] = run_kmedoids(peaks)
+        if rank == 0:
+            cfgs["4"]["posterior_kernel_other_shapes"] = [run_posterior_shape("M32", 10, peaks),
+                                                          run_posterior_shape("M52", 12, peaks)]
+    if 5 in wanted:
+        cfgs["5"] = run_reification_kg("config #5: full iteration (TM-stage grid) 1e6 candidates x 1000 hyper-parameter "
+                                       "sets, 3 ROMs + truth GP, M52, KG, then dedupe + kmedoids_max", 10 ** 6, 1000,
+                                       peaks, n_check=4, reps=1)
+
+    if rank == 0:
+        dgemm, dmma = peaks["dgemm"], peaks["dmma"]
         flop_per_launch = float(N_CAND) * (N_TRAIN ** 2 + N_TRAIN * (3 * N_DIM + 6))
         k_ms = float(np.mean(kern_ms))
         achieved = flop_per_launch / (k_ms * 1e-3) / 1e12
@@ -310,17 +595,21 @@ def run_gpu(args):
                     "frac": achieved / dgemm, "traffic": None, "kernel": "bf_posterior_dual_kernel<6,3>",
                     "kernel_ms": k_ms, "kernel_share_of_step": k_ms * len(kern_ms) / ms,
                     "flop_per_launch": flop_per_launch,
-                    "peak_source": "cuBLAS DGEMM 8192^3 (FP64 DMMA) measured in this run, best of 5; "
-                                   "MEASURED_PEAKS.json holds no FP64 figure"}
+                    "peak_source": "cuBLAS DGEMM 8192^3 measured in this run, best of 5 (cuBLAS dispatches "
+                                   "cutlass_80_tensorop_d884gemm, an sm_80 DMMA kernel); MEASURED_PEAKS.json holds no "
+                                   "FP64 figure",
+                    "peak_dmma_probe": dmma, "frac_of_dmma_probe": achieved / dmma,
+                    "peak_dmma_probe_source": "bf_probe_dmma in this run: 148 CTAs x 8 warps x 12 independent "
+                                              "mma.sync.m8n8k4.f64 chains (the DMMA pipe's issue rate), best of 5"}
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tr):      # dram__bytes_read+write per launch from the committed ncu --set full capture
             for k, v in json.load(open(tr)).items():
                 if k.startswith("bf_posterior"):
                     roofline["traffic"] = v["dram_bytes_per_launch"]
-                    roofline["traffic_source"] = v["source"]
-        peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.isfile(peaks):
-            roofline["hbm_gbs_measured"] = json.load(open(peaks)).get("hbm_gbs")
+                    roofline["traffic_source"] = v["source"] + " (a committed capture, not measured in this run)"
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.isfile(peaks_file):
+            roofline["hbm_gbs_measured"] = json.load(open(peaks_file)).get("hbm_gbs")
         cpu_steps = 2
         cpu_val, parity = None, None
         if world == 1:                                                       # N = 1 only (contract)
@@ -340,13 +629,26 @@ def run_gpu(args):
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / steps},
                 "roofline": roofline,
                 "cpu_baseline": cpu_baseline_dict(cpu_val, CPU_SAMPLE, cpu_steps) if world == 1 else None,
+                "cpu_baseline_verbatim_reference": verbatim_reference_record(),
                 "selected": {"EI": int(out[1][0]), "PI": int(out[1][1]), "UCB": int(out[1][2])},
                 "selected_e2e": {"EI": int(out_e2e[1][0]), "PI": int(out_e2e[1][1]), "UCB": int(out_e2e[1][2])},
-                "parity_vs_cpu_oracle": parity}
+                "parity_vs_cpu_oracle": parity, "configs": cfgs}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def verbatim_reference_record():
+    """SURVEY 8d baseline (i): the UNMODIFIED reference (multiNode=0, process pool on all cores) can only run
+    where /root/reference exists - the build container, never the GPU box - so it is timed there by
+    tools/time_reference_verbatim.py and the committed record is quoted here, labelled as such."""
+    path = os.path.join(ROOT, "profiles", "r2_reference_verbatim_cpu.json")
+    if not os.path.isfile(path):
+        return None
+    rec = json.load(open(path))
+    rec["note"] = "timed in the build container (the reference's sources are not on the GPU box), not in this run"
+    return rec
 
 
 def main():
@@ -355,6 +657,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--configs", default="", help="comma list of BASELINE configs to run besides the headline "
+                                                  "(default 2,3,4 and 5 at --gpus 8)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -201,6 +201,8 @@ int bf_reification(int m, long long P, const double* y, const double* var,
                    double* mean_f, double* var_f, void* stream);
 
 /* ---- (5) k-medoids primitives for kmedoids_max: util.py:38-49 (sklearn_extra KMedoids) ------ */
+/* Every distance is sklearn's pairwise_distances(X, metric="euclidean") value, i.e. the EXPANDED form
+ * sqrt(max(-2 x.y + |x|^2 + |y|^2, 0)) with a zero diagonal, operation for operation (bf_kmedoids.cu). */
 /* rowsum[i] = sum_j |x_i - x_j| for rows [row0, row0 + rows) against all N rows. */
 int bf_kmedoids_rowsum(long long N, int f, const double* X, long long row0, long long rows,
                        double* rowsum, void* stream);
@@ -227,6 +229,21 @@ int bf_kmedoids_sort_labels(long long N, int k, const int32_t* labels, long long
 int bf_kmedoids_update(long long N, int k, const long long* perm, const long long* seg,
                        const double* cost, long long* medoid_idx, int32_t* changed, void* stream);
 
+/* The update when the cost chunks are split over nparts ranks: records [k x 3] = per cluster (smallest cost
+ * among this part's positions, that position, cost at the current medoid's position if it is in this part),
+ * +inf for "none".  The ranks all-gather their records ([nparts x k x 3]) and bf_kmedoids_update_final
+ * applies the first-argmin / strictly-better rule; the result does not depend on nparts. */
+int bf_kmedoids_update_partial(long long N, int k, const long long* perm, const long long* seg,
+                               const double* cost, const long long* medoid_idx, int part, int nparts,
+                               double* records, void* stream);
+int bf_kmedoids_update_final(int k, int nparts, const double* records, const long long* perm,
+                             long long* medoid_idx, int32_t* changed, void* stream);
+/* One iteration of the alternate loop in one call: assign, sort_labels, cluster_cost_part, then update
+ * (nparts == 1) or update_partial (nparts > 1, records required). */
+int bf_kmedoids_iteration(long long N, int f, int k, const double* X, long long* medoid_idx,
+                          int32_t* labels, long long* perm, long long* seg, void* workspace, int part,
+                          int nparts, double* cost, double* records, int32_t* changed, void* stream);
+
 /* ---- clustering glue: barefoot.__kg_calc_clustering, barefoot.py:2102-2140 ---------------------- */
 /* Records r < R carry key[r] in [0, G) (selected candidate x* and model folded into one key) and
  * value[r].  Per group, the reference's in-order scan: the first record sets (value, row), a later one
@@ -247,6 +264,12 @@ int bf_total_variance(long long n, const double* err_mu, double err_std, double 
  * z = (f - mean) / std; zerr = |v / std^2|^0.5; stats[0] = mean, stats[1] = std. */
 int bf_zscore_targets(int n, const double* f_mean, const double* f_var, double* z, double* zerr,
                       double* stats, void* stream);
+
+/* ---- measurement aid: FP64 tensor (DMMA) issue rate, the roofline denominator bench.py quotes next to
+ * cuBLAS DGEMM.  ctas CTAs of 8 warps x 12 accumulator chains x iters mma.sync.m8n8k4.f64; out receives
+ * ctas * 256 doubles; bf_probe_dmma_flop = flop of one such launch. */
+double bf_probe_dmma_flop(int ctas, int iters);
+int bf_probe_dmma(int ctas, int iters, double* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -146,6 +146,31 @@ def test_config3_and_5_kg_over_fused_gps(eng, N, H):
     assert np.array_equal(kv2.cpu().numpy(), kv[perm]) and np.array_equal(ki2.cpu().numpy(), ki[perm])
 
 
+@pytest.mark.parametrize("f", [3, 2])
+def test_config4_kmedoids_full_size_equals_the_blocked_oracle(eng, f):
+    """BASELINE config #4 at full size (N' = 1e5, k = 10; f = 3 ROM-stage rows, f = 2 TM-stage rows): medoids,
+    labels, iteration count and the kmedoids_max output equal the golden result of the blocked restatement of
+    sklearn_extra's KMedoids (oracle/gen_kmedoids_full.py: every distance from scikit-learn's own
+    euclidean_distances - the expanded form the kernels reproduce operation for operation)."""
+    import os
+    from conftest import GOLDEN, golden
+    from barefoot_framework_b200 import util
+    if not os.path.isfile(os.path.join(GOLDEN, "kmedoids_full.npz")):
+        pytest.skip("tests/golden/kmedoids_full.npz not generated")
+    g = golden("kmedoids_full.npz")
+    N, k = int(g["N"]), int(g["k"])
+    rng = np.random.default_rng(int(g["seed"]))
+    cols = [np.exp(rng.normal(size=N)), rng.integers(0, 10 ** 6, size=N).astype(float),
+            rng.integers(0, 3, size=N).astype(float)]
+    X = np.ascontiguousarray(np.column_stack(cols[:f]))
+    np.testing.assert_array_equal(np.array([X.sum(), (X * np.arange(1, f + 1)).sum()]), g["f%d_x_checksum" % f])
+    med, labels, n_iter = eng.kmedoids_fit(X, k)
+    np.testing.assert_array_equal(med, g["f%d_medoids" % f])
+    assert n_iter == int(g["f%d_n_iter" % f])
+    np.testing.assert_array_equal(labels, g["f%d_labels" % f].astype(np.int64))
+    np.testing.assert_array_equal(util.kmedoids_max(X, k), g["f%d_kmedoids_max" % f])
+
+
 def test_config4_kmedoids_fixed_point_at_full_size(eng):
     rng = np.random.default_rng(0)
     N, k = 10 ** 5, 10
@@ -154,7 +179,7 @@ def test_config4_kmedoids_fixed_point_at_full_size(eng):
     rs = eng.kmedoids_rowsum(X).cpu().numpy()
     pick = rng.choice(N, size=64, replace=False)
     ref = np.array([np.sqrt(((X[i] - X) ** 2).sum(axis=1)).sum() for i in pick])
-    np.testing.assert_allclose(rs[pick], ref, rtol=1e-10)
+    np.testing.assert_allclose(rs[pick], ref, rtol=1e-10)       # direct form: equal to the expanded form in the SUM
     med, labels, n_iter = eng.kmedoids_fit(X, k)
     assert n_iter < 300 and len(set(med.tolist())) == k
     # labels = first arg-min over the medoids (np.argmin(D[medoids, :], axis=0))

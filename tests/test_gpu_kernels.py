@@ -149,8 +149,17 @@ def test_solve_path_matches_oracle_and_the_inverse_path(eng, kern, n, d, N):
         ucb = mu[s_] + 0.5 * var[s_]
         assert bi[s_, 2] == int(np.where(ucb == ucb.max())[0][0])
         assert bi[s_, 3] == int(np.where(mu[s_] == mu[s_].max())[0][0])
-    same = bi == b.best_idx.cpu().numpy()
-    assert same.mean() >= 0.9
+    # the explicit-inverse kernel must select the same candidates; where it does not, the two candidates must
+    # tie within the value tolerance (their values differ by rounding only)
+    from scipy.stats import norm
+    bj = b.best_idx.cpu().numpy()
+    for s_ in range(S):
+        vals = [(mu[s_] - 0.3 - 0.01) * norm.pdf(mu[s_]) + var[s_] * norm.cdf(mu[s_]),
+                norm.cdf((mu[s_] - 0.3 - 0.01) / var[s_]), mu[s_] + 0.5 * var[s_], mu[s_]]
+        for slot in range(4):
+            if bi[s_, slot] != bj[s_, slot]:
+                va, vb = vals[slot][bi[s_, slot]], vals[slot][bj[s_, slot]]
+                assert abs(va - vb) <= REL * max(1.0, abs(va)), (s_, slot, va, vb)
 
 
 def test_kernel_matrix_lower_writes_only_the_blocks_the_factorisation_reads(eng):
