@@ -519,6 +519,28 @@ def zscore_targets(f_mean, f_var):
     return z, zerr, stats
 
 
+def zscore_targets_batched(f_mean, f_var):
+    """zscore_targets for G groups at once: f_mean, f_var [G, n] -> (z [G, n], zerr [G, n], stats [G, 2])."""
+    G, n = f_mean.shape
+    z = torch.empty_like(f_mean)
+    zerr = torch.empty_like(f_mean)
+    stats = torch.empty((G, 2), dtype=F64, device=f_mean.device)
+    call("bf_zscore_targets_batched", G, n, ptr(f_mean), ptr(f_var), ptr(z), ptr(zerr), ptr(stats), stream())
+    return z, zerr, stats
+
+
+def fantasy_rows(mu_f, var_f, C, mu_t, var_t, y_new, noise_var, gp_mean, model_std, model_mean, err_term):
+    """bf_fantasy_rows: the de-normalised mean / total-variance rows [K, F] of one ROM after appending each of K
+    fantasy points in turn (bordered form of gp_model.update, gpModel.py:56-64)."""
+    F, K = mu_f.numel(), mu_t.numel()
+    mean_rows = torch.empty((K, F), dtype=F64, device=mu_f.device)
+    var_rows = torch.empty((K, F), dtype=F64, device=mu_f.device)
+    call("bf_fantasy_rows", F, K, ptr(mu_f), ptr(var_f), ptr(C), C.stride(0), ptr(mu_t), ptr(var_t), ptr(y_new),
+         float(noise_var), float(gp_mean), float(model_std), float(model_mean), ptr(err_term), ptr(mean_rows),
+         ptr(var_rows), stream())
+    return mean_rows, var_rows
+
+
 # ---- k-medoids (util.py:38-49) -----------------------------------------------------------------
 def kmedoids_rowsum(X, row0=0, rows=None):
     Xd = to_dev(X)

@@ -111,6 +111,39 @@ class model_reification():
         f_mean, f_var = engine.reification(means, variances)
         return engine.zscore_targets(f_mean, f_var)
 
+    def fantasy_targets_batched(self, x_fused, x_new, y_new, jj, base_means, base_vars):
+        """The fused-GP targets after ROM `jj` has been updated with (x_new[k], y_new[k]) - for each k in turn,
+        all K at once and without building K updated GPs: util.py:243-246 calls update_GP (append one point,
+        refactor, gpModel.py:56-64) and create_fused_GP per work item; here the appended factor is taken in its
+        bordered form (bf_fantasy_rows), the other m - 1 rows and every discrepancy GP are the un-updated
+        model's (base_means / base_vars from fused_rows_device), and reification + z-scoring run over all K
+        groups in one launch each.  Returns (z [K, F], zerr [K, F], stats [K, 2])."""
+        g, e = self.gp_models[jj], self.gp_err_models[jj]
+        xf = engine.to_dev(np.asarray(x_fused, dtype=np.float64).reshape(len(x_fused), -1))
+        xt = engine.to_dev(np.asarray(x_new, dtype=np.float64).reshape(len(x_new), -1))
+        m, F, K = base_means.shape[0], xf.shape[0], xt.shape[0]
+        std_j, mean_j = float(self.model_std[jj]), float(self.model_mean[jj])
+        rf = engine.posterior_sweep(g.gp, xf, want_mu=True, want_var=True)
+        rt = engine.posterior_sweep(g.gp, xt, want_mu=True, want_var=True)
+        _, C = engine.posterior_cov(g.gp, xf, xt)                                   # [F, K]
+        er = engine.posterior_sweep(e.gp, xf, want_mu=True)
+        emu = er.mu[0] if not e.mean else er.mu[0] + float(e.mean)
+        err_term = engine.total_variance(emu, float(self.err_std[jj]), float(self.err_mean[jj]),
+                                         torch.zeros_like(emu), 0.0)                # (err_mu * err_std + err_mean)^2
+        y = (np.asarray(y_new, dtype=np.float64).reshape(-1) - mean_j) / std_j - float(g.mean)   # update_GP's normalisation
+        sn = np.asarray(g.sigma_n, dtype=np.float64)
+        if sn.size != 1:
+            raise ValueError("fantasy_targets_batched needs a scalar sigma_n for the ROM GPs (reificationFusion.py:176)")
+        noise_var = float(np.sqrt(float(sn.reshape(-1)[0]) ** 2 + 1.25e-12) ** 2)     # george: (yerr^2 + TINY) on the diagonal
+        mean_rows, var_rows = engine.fantasy_rows(rf.mu[0].contiguous(), rf.var[0].contiguous(), C, rt.mu[0].contiguous(),
+                                                  rt.var[0].contiguous(), engine.to_dev(y), noise_var, float(g.mean),
+                                                  std_j, mean_j, err_term)
+        Y = base_means.unsqueeze(1).expand(m, K, F).clone()
+        V = base_vars.unsqueeze(1).expand(m, K, F).clone()
+        Y[jj], V[jj] = mean_rows, var_rows
+        f_mean, f_var = engine.reification(Y.view(m, K * F), V.view(m, K * F))
+        return engine.zscore_targets_batched(f_mean.view(K, F), f_var.view(K, F))
+
     def fused_targets_device(self, x_test):
         """reificationFusion.py:143-159 on the device: the 2m posteriors at x_test, the
         de-normalisation, total variance, reification and z-scoring.  Returns

@@ -151,7 +151,7 @@ def fused_calculate(param):
 # ---------------------------------------------------------------------------------------------
 def rom_stage_batch(model, x_fused, hp_sets, kernel, x_test, new_mean, acq, cost, curr_max,
                     iteration=1, true_sample_count=None, jj_list=None, kk_list=None, as_arrays=False,
-                    max_bytes_in_flight=16 << 30, solve_path=None):
+                    max_bytes_in_flight=16 << 30, solve_path=None, fantasy="append"):
     """The ROM-stage grid of barefoot.py:1001-1073: for every model jj, fantasy point kk and
     hyper-parameter set mm, update ROM jj with (x_test[kk], new_mean[jj][kk]), rebuild the fused
     GP and evaluate `acq` over x_test.  Returns the rows [max fused mean, value / cost[jj], x*,
@@ -159,6 +159,9 @@ def rom_stage_batch(model, x_fused, hp_sets, kernel, x_test, new_mean, acq, cost
     For "Hedge" returns six such row lists in the portfolio order [KG, TS, EI, Greedy, PI, UCB].
     as_arrays=True returns float64 arrays [G * H, 6 (+ 2 d for Greedy)] instead of lists of rows.
     solve_path: None = automatic (few candidates per fused GP -> engine.SolveSpec, else explicit factors).
+    fantasy: "append" (default) = all fantasy updates of a model at once through the bordered form of the
+    appended Cholesky factor (model_reification.fantasy_targets_batched); "refactor" = the reference's literal
+    per-group update_GP (append + full refactor) in a host loop - the same numbers to rounding.
 
     The fused targets of one (jj, kk) do not depend on mm; the H fused GPs of every (jj, kk)
     are factorised and swept together (one set per (jj, kk, mm))."""
@@ -193,23 +196,42 @@ def rom_stage_batch(model, x_fused, hp_sets, kernel, x_test, new_mean, acq, cost
         base_means, base_vars = model.fused_rows_device(x_fused)
         for g0 in range(0, G, groups_per_chunk):
             chunk = keys[g0:g0 + groups_per_chunk]
-            zs, zerrs, stats = [], [], []
-            for (jj, kk) in chunk:
-                m2 = _fantasy_copy(model, copy)
-                m2.update_GP(np.expand_dims(x_test[kk], axis=0), np.expand_dims(np.array([new_mean[jj][kk]]), axis=0), jj)
-                # only ROM jj changed: its row is recomputed, the other rows (and every discrepancy GP) are the
-                # unmodified model's (util.py:243-246 recomputes all 2m posteriors per work item)
-                mj, vj = m2.fused_rows_device(x_fused, models=[jj])
-                means, variances = base_means.clone(), base_vars.clone()
-                means[jj], variances[jj] = mj[0], vj[0]
-                z, zerr, st = m2.fused_targets_from_rows(means, variances)
-                zs.append(z)
-                zerrs.append(zerr)
-                stats.append(st)
+            if fantasy == "refactor":
+                zs, zerrs, stats = [], [], []
+                for (jj, kk) in chunk:
+                    # the reference's literal step: a private copy of the model, update_GP (append + full refactor)
+                    m2 = _fantasy_copy(model, copy)
+                    m2.update_GP(np.expand_dims(x_test[kk], axis=0), np.expand_dims(np.array([new_mean[jj][kk]]), axis=0), jj)
+                    # only ROM jj changed: its row is recomputed, the other rows (and every discrepancy GP) are the
+                    # unmodified model's (util.py:243-246 recomputes all 2m posteriors per work item)
+                    mj, vj = m2.fused_rows_device(x_fused, models=[jj])
+                    means, variances = base_means.clone(), base_vars.clone()
+                    means[jj], variances[jj] = mj[0], vj[0]
+                    z, zerr, st = m2.fused_targets_from_rows(means, variances)
+                    zs.append(z)
+                    zerrs.append(zerr)
+                    stats.append(st)
+                Zg, ZEg, ST = torch.stack(zs), torch.stack(zerrs), torch.stack(stats)
+            else:
+                # all fantasy points of a model in one launch sequence (bordered append, no per-group host work)
+                zs, zerrs, stats = [], [], []
+                a = 0
+                while a < len(chunk):
+                    jj = chunk[a][0]
+                    b = a
+                    while b < len(chunk) and chunk[b][0] == jj:
+                        b += 1
+                    kks = [kk for _, kk in chunk[a:b]]
+                    z, zerr, st = model.fantasy_targets_batched(x_fused, x_test[kks], [new_mean[jj][kk] for kk in kks],
+                                                                jj, base_means, base_vars)
+                    zs.append(z)
+                    zerrs.append(zerr)
+                    stats.append(st)
+                    a = b
+                Zg, ZEg, ST = torch.cat(zs), torch.cat(zerrs), torch.cat(stats)
             Gc = len(chunk)
-            Z = torch.stack(zs).repeat_interleave(H, dim=0).contiguous()          # [Gc*H, F]
-            ZE = torch.stack(zerrs).repeat_interleave(H, dim=0).contiguous()
-            ST = torch.stack(stats)                                               # [Gc, 2] (mean, std)
+            Z = Zg.repeat_interleave(H, dim=0).contiguous()                       # [Gc*H, F]
+            ZE = ZEg.repeat_interleave(H, dim=0).contiguous()                     # ST: [Gc, 2] (mean, std)
             scale = ST[:, 1].repeat_interleave(H).contiguous()
             shift = ST[:, 0].repeat_interleave(H).contiguous()
             set_hp = np.tile(np.arange(H, dtype=np.int32), Gc)

@@ -265,6 +265,21 @@ int bf_total_variance(long long n, const double* err_mu, double err_std, double 
 int bf_zscore_targets(int n, const double* f_mean, const double* f_var, double* z, double* zerr,
                       double* stats, void* stream);
 
+/* G independent z-scorings (f_mean, f_var, z, zerr: [G x n]; stats [G x 2]): bf_zscore_targets per group. */
+int bf_zscore_targets_batched(int G, int n, const double* f_mean, const double* f_var, double* z,
+                              double* zerr, double* stats, void* stream);
+/* ROM-stage fantasy updates (util.py:243 -> reificationFusion.py:169-178 -> gpModel.py:56-64: append one point
+ * and refactor) for K fantasy points of ONE model at once, as the bordered (rank-one) form of the appended
+ * factor.  Inputs in the GP's normalised units from the UN-updated GP: mu_f, var_f [F] at the fused points;
+ * mu_t, var_t [K] at the fantasy points; C [F x ldc] posterior covariance between them (bf_gp_cov); y_new [K]
+ * the normalised fantasy targets (minus the GP's constant mean); noise_var = sigma_n^2 + 1.25e-12.
+ * Outputs [K x F]: the de-normalised mean row and the total variance row (err_term [F] + var' model_std^2) that
+ * reification consumes (reificationFusion.py:147-152). */
+int bf_fantasy_rows(int F, int K, const double* mu_f, const double* var_f, const double* C, long long ldc,
+                    const double* mu_t, const double* var_t, const double* y_new, double noise_var,
+                    double gp_mean, double model_std, double model_mean, const double* err_term,
+                    double* mean_rows, double* var_rows, void* stream);
+
 /* ---- measurement aid: FP64 tensor (DMMA) issue rate, the roofline denominator bench.py quotes next to
  * cuBLAS DGEMM.  ctas CTAs of 8 warps x 12 accumulator chains x iters mma.sync.m8n8k4.f64; out receives
  * ctas * 256 doubles; bf_probe_dmma_flop = flop of one such launch. */

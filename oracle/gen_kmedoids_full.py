@@ -32,7 +32,7 @@ def main():
     for f in (3, 2):
         X = make_rows(N, f)
         t0 = time.time()
-        med, labels, n_iter = kb.fit(X, k, verbose=True)
+        med, labels, n_iter = kb.fit(X, k, verbose=True, workers=min(k, os.cpu_count() or 1))
         picks = []
         for c in range(k):
             members = X[labels == c, 0]

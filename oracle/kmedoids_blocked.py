@@ -18,13 +18,17 @@ from sklearn.metrics.pairwise import euclidean_distances
 from sklearn.utils.extmath import row_norms
 
 
-def _rows(X, XX, r_idx, c_idx=None):
-    """D[r_idx][:, c_idx] (c_idx None = all columns), rows = r_idx."""
+def _rows(X, XX, r_idx, c_idx=None, diag=None):
+    """D[r_idx][:, c_idx] (c_idx None = all columns), rows = r_idx.  `diag` = (rows, cols) positions of this
+    block that lie on the diagonal of the full matrix (filled with 0 there); None = find them by comparison."""
     Y = X if c_idx is None else X[c_idx]
     YY = XX if c_idx is None else XX[c_idx]
     D = euclidean_distances(X[r_idx], Y, X_norm_squared=XX[r_idx], Y_norm_squared=YY)
-    cols = np.arange(X.shape[0]) if c_idx is None else np.asarray(c_idx)
-    D[np.asarray(r_idx)[:, None] == cols[None, :]] = 0.0          # the filled diagonal of the full matrix
+    if diag is None:
+        cols = np.arange(X.shape[0]) if c_idx is None else np.asarray(c_idx)
+        D[np.asarray(r_idx)[:, None] == cols[None, :]] = 0.0      # the filled diagonal of the full matrix
+    else:
+        D[diag] = 0.0
     return D
 
 
@@ -34,7 +38,7 @@ def row_sums(X, block=2048):
     out = np.empty(X.shape[0])
     for r0 in range(0, X.shape[0], block):
         r = np.arange(r0, min(r0 + block, X.shape[0]))
-        out[r] = _rows(X, XX, r).sum(axis=1)
+        out[r] = _rows(X, XX, r, diag=(np.arange(r.shape[0]), r)).sum(axis=1)
     return out
 
 
@@ -47,13 +51,31 @@ def cluster_costs(X, XX, idx, block=1024):
     costs = np.empty(idx.shape[0])
     for a0 in range(0, idx.shape[0], block):
         a = idx[a0:a0 + block]
-        E = _rows(X, XX, idx, a)                                  # E[b, a] = D[idx[b], idx[a]]
+        j = np.arange(a.shape[0])
+        E = _rows(X, XX, idx, a, diag=(a0 + j, j))                # E[b, a] = D[idx[b], idx[a]] (idx is duplicate free)
         costs[a0:a0 + block] = np.ascontiguousarray(E.T).sum(axis=1)
     return costs
 
 
-def fit(X, k, max_iter=300, verbose=False):
-    """KMedoids(n_clusters=k, random_state=0).fit(X) -> (medoid_indices_, labels_, n_iter_)."""
+_SHARED = {}
+
+
+def _cluster_task(c):
+    """One cluster of one alternate iteration (run in a forked worker): new medoid or -1."""
+    X, XX, labels, med = _SHARED["X"], _SHARED["XX"], _SHARED["labels"], _SHARED["med"]
+    idx = np.where(labels == c)[0]
+    if len(idx) == 0:
+        return -1
+    costs = cluster_costs(X, XX, idx)
+    j = np.argmin(costs)
+    if costs[j] < costs[np.argmax(idx == med[c])]:
+        return int(idx[j])
+    return -1
+
+
+def fit(X, k, max_iter=300, verbose=False, workers=1):
+    """KMedoids(n_clusters=k, random_state=0).fit(X) -> (medoid_indices_, labels_, n_iter_).  workers > 1: the
+    clusters of an iteration (independent of each other) are evaluated by forked worker processes."""
     X = np.ascontiguousarray(X, dtype=np.float64)
     XX = row_norms(X, squared=True)
     med = np.argpartition(row_sums(X), k - 1)[:k]
@@ -61,14 +83,16 @@ def fit(X, k, max_iter=300, verbose=False):
     for n_iter in range(max_iter):
         old = med.copy()
         labels = labels_of(X, XX, med)
-        for c in range(k):
-            idx = np.where(labels == c)[0]
-            if len(idx) == 0:
-                continue
-            costs = cluster_costs(X, XX, idx)
-            j = np.argmin(costs)
-            if costs[j] < costs[np.argmax(idx == med[c])]:
-                med[c] = idx[j]
+        _SHARED.update(X=X, XX=XX, labels=labels, med=old)
+        if workers > 1:
+            import multiprocessing
+            with multiprocessing.get_context("fork").Pool(workers) as pool:
+                moved = pool.map(_cluster_task, range(k))
+        else:
+            moved = [_cluster_task(c) for c in range(k)]
+        for c, new in enumerate(moved):
+            if new >= 0:
+                med[c] = new
         if verbose:
             print("iteration", n_iter + 1, "moved", int(np.sum(old != med)), flush=True)
         if np.all(old == med):

@@ -135,9 +135,13 @@ def test_tm_stage_batch(pkg, cidx):
         np.testing.assert_allclose(vals, g[pre + f"tm_{opt}_val"], rtol=1e-8, atol=1e-11, err_msg=opt)
 
 
+@pytest.mark.parametrize("fantasy", ["append", "refactor"])
 @pytest.mark.parametrize("solve_path", [False, True])
 @pytest.mark.parametrize("cidx", [0, 1, 2, 3])
-def test_rom_stage_batch(pkg, cidx, solve_path):
+def test_rom_stage_batch(pkg, cidx, solve_path, fantasy):
+    """Work-item goldens of the verbatim calculate_* functions, through both set-up paths and both forms of the
+    fantasy update: "refactor" = update_GP per (model, fantasy point) as the reference does, "append" = all
+    fantasy points of a model at once through the bordered form of the appended factor."""
     g = golden("workitems.npz")
     pre = f"c{cidx}_"
     kern = str(g[pre + "kern"])
@@ -148,7 +152,7 @@ def test_rom_stage_batch(pkg, cidx, solve_path):
     for opt in ("KG", "EI", "PI", "UCB", "Greedy"):
         rows = pkg.util.rom_stage_batch(model, x_fused, hps, kern, x_test, new_mean, opt, costs,
                                         float(g[pre + "curr_max"]), iteration=3, true_sample_count=x_test.shape[0],
-                                        kk_list=list(g[pre + "rom_kks"]), solve_path=solve_path)
+                                        kk_list=list(g[pre + "rom_kks"]), solve_path=solve_path, fantasy=fantasy)
         ref = g[pre + f"rom_{opt}"]
         rows = np.array(rows, dtype=np.float64)
         assert rows.shape == ref.shape
