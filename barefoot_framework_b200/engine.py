@@ -102,6 +102,26 @@ def section_ms(name):
     return sum(a.elapsed_time(b) for nm, a, b in (timeline or []) if nm == name)
 
 
+# Factorisation kernel choice: "auto" = the fused left-looking kernel (bf_cholesky_fused: kernel tiles generated
+# into the accumulators, no K in HBM, several sets per SM) for many sets, the right-looking shared-memory-panel
+# kernel (bf_kernel_matrix_lower + bf_cholesky_batched) for a few; "ll" / "rl" force one (measurements, tests).
+CHOLESKY = "auto"
+FUSED_MIN_SETS = 32
+POISON_SCRATCH = False      # tests: fill the factor scratch with NaN first (no consumer may read an unwritten block)
+
+
+def _scratch(shape, dev):
+    if POISON_SCRATCH:
+        return torch.full(shape, float("nan"), dtype=F64, device=dev)
+    return torch.empty(shape, dtype=F64, device=dev)
+
+
+def _use_fused(n, d, S):
+    if CHOLESKY == "rl" or not _lib.load().bf_cholesky_fused_supported(int(n), int(d)):
+        return False
+    return CHOLESKY == "ll" or S >= FUSED_MIN_SETS
+
+
 class GPFactors:
     """Factorised GPs sharing the training inputs X: one "set" per hyper-parameter
     set (and, in the ROM stage, per fantasy point)."""
@@ -162,7 +182,7 @@ def build_factors(kern, X, y, l_sq, sigma_f, yerr, ndim=None, set_hp=None, n_set
     info = torch.zeros((S,), dtype=torch.int32, device=dev)
     per_set = 2 * np_ * np_ * 8
     chunk = S if keep_dense else max(1, min(S, 65535, chunk_bytes // per_set))
-    Lbuf = torch.empty((chunk, np_, np_), dtype=F64, device=dev)
+    Lbuf = _scratch((chunk, np_, np_), dev)
     Libuf = torch.empty((chunk, np_, np_), dtype=F64, device=dev)
     st = stream()
     with _Section("setup"):
@@ -172,9 +192,14 @@ def build_factors(kern, X, y, l_sq, sigma_f, yerr, ndim=None, set_hp=None, n_set
             inv_p, amp_p = inv_l2, amp
             if hp_t is None:    # identity map: shift the HP rows instead
                 inv_p, amp_p = inv_l2[s0:], amp[s0:]
-            call("bf_kernel_matrix_lower", KERN[kern], n, d, sc, ptr(X), inv_p.data_ptr(), amp_p.data_ptr(), hp_p,
-                 yerr_t[s0:].data_ptr() if yerr_stride else ptr(yerr_t), yerr_n, yerr_stride, ptr(Lbuf), st)
-            call("bf_cholesky_batched", n, sc, ptr(Lbuf), info[s0:].data_ptr(), st)
+            yerr_p = yerr_t[s0:].data_ptr() if yerr_stride else ptr(yerr_t)
+            if _use_fused(n, d, sc):
+                call("bf_cholesky_fused", KERN[kern], n, d, sc, ptr(X), inv_p.data_ptr(), amp_p.data_ptr(), hp_p, yerr_p,
+                     yerr_n, yerr_stride, ptr(Lbuf), info[s0:].data_ptr(), None, int(bool(keep_dense)), st)
+            else:
+                call("bf_kernel_matrix_lower", KERN[kern], n, d, sc, ptr(X), inv_p.data_ptr(), amp_p.data_ptr(), hp_p,
+                     yerr_p, yerr_n, yerr_stride, ptr(Lbuf), st)
+                call("bf_cholesky_batched", n, sc, ptr(Lbuf), info[s0:].data_ptr(), st)
             call("bf_factor_finish", n, sc, ptr(Lbuf), y[s0:].data_ptr() if y_stride else ptr(y), y_stride,
                  ptr(Libuf), linv_packed[s0:].data_ptr(), alpha[s0:].data_ptr(), st)
     f = GPFactors(kern, X, inv_l2, amp, hp_t, linv_packed, alpha, S,
@@ -242,7 +267,7 @@ def solve_sweep(f, Xs, scale=None, shift=None, want_mu=False, want_var=False, ac
     parts = lib.bf_posterior_solve_parts(n, N)
     per_set = 8 * (np_ * np_ + nb * 1024)
     chunk = max(1, min(S, 65535, f.chunk_bytes // per_set))
-    Lbuf = torch.empty((chunk, np_, np_), dtype=F64, device=dev)
+    Lbuf = _scratch((chunk, np_, np_), dev)
     dinv = torch.empty((chunk, nb, 32, 32), dtype=F64, device=dev)
     info = torch.zeros((S,), dtype=torch.int32, device=dev)
     pv = pi = None
@@ -255,14 +280,24 @@ def solve_sweep(f, Xs, scale=None, shift=None, want_mu=False, want_var=False, ac
         hp_p = None if f.set_hp is None else f.set_hp[s0:].data_ptr()
         inv_p = f.inv_l2 if f.set_hp is not None else f.inv_l2[s0:]
         amp_p = f.amp if f.set_hp is not None else f.amp[s0:]
-        call("bf_kernel_matrix_lower", KERN[f.kern], n, d, sc, ptr(f.X), inv_p.data_ptr(), amp_p.data_ptr(), hp_p,
-             f.yerr[s0:].data_ptr() if f.yerr_stride else ptr(f.yerr), f.yerr_n, f.yerr_stride, ptr(Lbuf), st)
-        call("bf_cholesky_batched_dinv", n, sc, ptr(Lbuf), info[s0:].data_ptr(), ptr(dinv), st)
+        yerr_p = f.yerr[s0:].data_ptr() if f.yerr_stride else ptr(f.yerr)
+        if _use_fused(n, d, sc):
+            with _Section("solve_cholesky_fused"):
+                call("bf_cholesky_fused", KERN[f.kern], n, d, sc, ptr(f.X), inv_p.data_ptr(), amp_p.data_ptr(), hp_p,
+                     yerr_p, f.yerr_n, f.yerr_stride, ptr(Lbuf), info[s0:].data_ptr(), ptr(dinv), 0, st)
+        else:
+            with _Section("solve_kernel_matrix"):
+                call("bf_kernel_matrix_lower", KERN[f.kern], n, d, sc, ptr(f.X), inv_p.data_ptr(), amp_p.data_ptr(),
+                     hp_p, yerr_p, f.yerr_n, f.yerr_stride, ptr(Lbuf), st)
+            with _Section("solve_cholesky"):
+                call("bf_cholesky_batched_dinv", n, sc, ptr(Lbuf), info[s0:].data_ptr(), ptr(dinv), st)
+        e_ps = _Section("solve_posterior").__enter__()
         call("bf_gp_posterior_solve", KERN[f.kern], N, n, d, sc, ptr(Xs), ptr(f.X), inv_p.data_ptr(), amp_p.data_ptr(),
              hp_p, ptr(Lbuf), ptr(dinv), f.y[s0:].data_ptr() if f.y_stride else ptr(f.y), f.y_stride,
              None if scale is None else scale[s0:].data_ptr(), None if shift is None else shift[s0:].data_ptr(),
              None if out.mu is None else out.mu[s0:].data_ptr(), None if out.var is None else out.var[s0:].data_ptr(),
              acq_mask, int(bool(spread_is_sqrt)), float(curr_max), float(xi), float(kt), ptr(pv), ptr(pi), st)
+        e_ps.__exit__()
         if acq_mask:
             call("bf_acq_finalize", sc, parts, acq_mask, ptr(pv), ptr(pi), out.best_val[s0:].data_ptr(),
                  out.best_idx[s0:].data_ptr(), st)

@@ -265,6 +265,18 @@ int bf_total_variance(long long n, const double* err_mu, double err_std, double 
 int bf_zscore_targets(int n, const double* f_mean, const double* f_var, double* z, double* zerr,
                       double* stats, void* stream);
 
+/* ---- fused kernel matrix + Cholesky for many sets (gpModel.py:38-42 per work item) -------------------- */
+/* L [S x np x np] <- chol(amp k(X, X) + diag(yerr^2 + 1.25e-12)) per set with the arguments of
+ * bf_kernel_matrix, without ever storing K: a left-looking blocked factorisation that generates the kernel
+ * tiles into its accumulators (bf_cholesky_ll.cu).  The 32 x 32 blocks strictly above the diagonal are left
+ * untouched unless zero_upper is set.  info [S] as bf_cholesky_batched; dinv (optional) as
+ * bf_cholesky_batched_dinv. */
+int bf_cholesky_fused_supported(int n, int d);
+int bf_cholesky_fused(int kern, int n, int d, int S, const double* X, const double* inv_l2,
+                      const double* amp, const int32_t* set_hp, const double* yerr, int yerr_n,
+                      long long yerr_stride, double* L, int32_t* info, double* dinv, int zero_upper,
+                      void* stream);
+
 /* G independent z-scorings (f_mean, f_var, z, zerr: [G x n]; stats [G x 2]): bf_zscore_targets per group. */
 int bf_zscore_targets_batched(int G, int n, const double* f_mean, const double* f_var, double* z,
                               double* zerr, double* stats, void* stream);

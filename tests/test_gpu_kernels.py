@@ -570,3 +570,74 @@ def test_new_kernels_stay_inside_their_output_buffers(eng, n, N):
     g.check()
     assert int(info.max()) == 0 and int(bad[0]) == 0
     assert bool(torch.isfinite(mu).all()) and bool(torch.isfinite(var).all()) and bool(torch.isfinite(alpha).all())
+
+
+# ---- fused left-looking Cholesky (bf_cholesky_fused) ----------------------------------------------------------
+@pytest.fixture
+def chol_mode(eng):
+    saved = (eng.CHOLESKY, eng.POISON_SCRATCH)
+    yield eng
+    eng.CHOLESKY, eng.POISON_SCRATCH = saved
+
+
+@pytest.mark.parametrize("kern", ["SE", "M32", "M52"])
+@pytest.mark.parametrize("n,d,S", [(5, 1, 3), (32, 2, 4), (33, 2, 5), (70, 3, 40), (200, 6, 7), (500, 6, 3), (700, 4, 2),
+                                   (96, 12, 5)])
+def test_fused_cholesky_equals_kernel_matrix_plus_right_looking(chol_mode, kern, n, d, S):
+    """bf_cholesky_fused (kernel tiles generated into the accumulators, left-looking, no K in memory) against
+    bf_kernel_matrix_lower + bf_cholesky_batched on the same sets: per-set noise, set -> hyper-parameter map,
+    identity padding, zeros above the diagonal, then L^-1 / alpha from either factor."""
+    eng = chol_mode
+    rng = np.random.default_rng(n * 13 + d + S)
+    X, _, _ = make_problem(rng, n, d, 4)
+    H = min(S, 3)
+    l = rng.uniform(0.2, 0.9, size=(H, d))
+    sf = rng.uniform(0.5, 3.0, size=H)
+    Y = rng.normal(size=(S, n))
+    YE = rng.uniform(0.03, 0.2, size=(S, n))
+    set_hp = (np.arange(S) % H).astype(np.int32)
+    eng.CHOLESKY = "rl"
+    a = eng.build_factors(kern, X, Y, l ** 2, sf, YE, set_hp=set_hp, keep_dense=True)
+    eng.CHOLESKY, eng.POISON_SCRATCH = "ll", True
+    b = eng.build_factors(kern, X, Y, l ** 2, sf, YE, set_hp=set_hp, keep_dense=True)
+    La, Lb = a.L.cpu().numpy(), b.L.cpu().numpy()
+    assert np.isfinite(Lb).all()
+    assert not np.triu(Lb, 1).any()
+    np_ = La.shape[1]
+    for s_ in range(S):
+        assert np.array_equal(Lb[s_, n:, n:], np.eye(np_ - n)) and not Lb[s_, n:, :n].any()
+        assert np.abs(La[s_] - Lb[s_]).max() <= 1e-12 * np.abs(La[s_]).max() * n
+    np.testing.assert_allclose(b.alpha.cpu().numpy(), a.alpha.cpu().numpy(), rtol=1e-8,
+                               atol=1e-9 * np.abs(a.alpha.cpu().numpy()).max())
+    for s_ in (0, S - 1):
+        g = fast.GP(X, Y[s_], l[set_hp[s_]], sf[set_hp[s_]], YE[s_], d, kern)
+        np.testing.assert_allclose(Lb[s_, :n, :n], np.linalg.cholesky(g.K), rtol=1e-10, atol=1e-12)
+
+
+def test_fused_cholesky_solve_path_never_reads_unwritten_blocks(chol_mode):
+    """The fused kernel leaves the blocks above the diagonal untouched; with the scratch poisoned by NaN the
+    solve path (L, diagonal-block inverses) and the explicit-inverse path must still match the oracle, and a
+    set that is not positive definite is reported."""
+    eng = chol_mode
+    rng = np.random.default_rng(77)
+    n, d, N, S = 300, 4, 20, 36
+    X, _, Xs = make_problem(rng, n, d, N)
+    l = rng.uniform(0.2, 0.9, size=(S, d))
+    sf = rng.uniform(0.5, 3.0, size=S)
+    Y = rng.normal(size=(S, n))
+    YE = rng.uniform(0.03, 0.2, size=(S, n))
+    eng.CHOLESKY, eng.POISON_SCRATCH = "ll", True
+    spec = eng.SolveSpec("M52", X, Y, l ** 2, sf, YE)
+    a = eng.posterior_sweep(spec, Xs, want_mu=True, want_var=True, acq_mask=15, curr_max=0.3, kt=0.5)
+    f = eng.build_factors("M52", X, Y, l ** 2, sf, YE)
+    b = eng.posterior_sweep(f, Xs, want_mu=True, want_var=True, acq_mask=15, curr_max=0.3, kt=0.5)
+    for s_ in (0, 17, S - 1):
+        g = fast.GP(X, Y[s_], l[s_], sf[s_], YE[s_], d, "M52")
+        mref, vref = g.predict_var(Xs)
+        for res in (a, b):
+            assert np.abs(res.mu[s_].cpu().numpy() - mref).max() <= REL * max(1.0, np.abs(mref).max())
+            assert np.abs(res.var[s_].cpu().numpy() - vref).max() <= REL * fast.amplitude(sf[s_], d)
+    bad = l.copy()
+    bad[S - 2, 0] = np.nan
+    with pytest.raises(np.linalg.LinAlgError):
+        eng.build_factors("M52", X, Y, bad ** 2, sf, YE)

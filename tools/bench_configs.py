@@ -159,11 +159,20 @@ def config_rom_stage(args, N, H):
     rom_stage_batch(model, x_fused, hps[:2], "M52", x_test[:3], new_mean, "KG", costs, float(y_true.max()),
                     true_sample_count=3, as_arrays=True)              # warm-up
     torch.cuda.synchronize()
+    engine.timeline = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    ev0.record()
     rows = rom_stage_batch(model, x_fused, hps, "M52", x_test, new_mean, "KG", costs, float(y_true.max()),
                            true_sample_count=N, as_arrays=True)
+    ev1.record()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
+    tl, engine.timeline = engine.timeline, None
+    sections = {}
+    for nm, a, b in tl:
+        sections[nm] = sections.get(nm, 0.0) + a.elapsed_time(b)
+    sections["first_to_last_event"] = ev0.elapsed_time(ev1)
     med_input = barefoot._cluster_rows(rows, m)
     k = min(5, med_input.shape[0])
     medoids = kmedoids_max(med_input[:, 0:3], k)
@@ -178,7 +187,7 @@ def config_rom_stage(args, N, H):
                       "candidates": N, "H": H, "F": F, "fused_gps": sets, "evals": sets * N,
                       "s": {"rom_stage": t1 - t0, "clustering_device": t2 - t1,
                             "clustering_reference_dict_loop_host": t_ref1 - t_ref0},
-                      "fused_gps_per_s": sets / (t1 - t0), "evals_per_s": sets * N / (t1 - t0),
+                      "device_ms_by_section": sections, "fused_gps_per_s": sets / (t1 - t0), "evals_per_s": sets * N / (t1 - t0),
                       "setup_tflops_chol_plus_inverse": sets * (2.0 * F ** 3 / 3.0) / (t1 - t0) / 1e12,
                       "cluster_rows": int(med_input.shape[0]),
                       "selected": [[int(rows[int(med_input[mm_, 3]), 2]), int(rows[int(med_input[mm_, 3]), 3])] for mm_ in medoids]}))
