@@ -63,6 +63,7 @@ SIGNATURES = {
     "bf_kmedoids_update_final": (c_i, [c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "bf_kmedoids_iteration": (c_i, [c_ll, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
     "bf_cholesky_fused_supported": (c_i, [c_i, c_i]),
+    "bf_cholesky_ll_inplace": (c_i, [c_i, c_i, c_p, c_p, c_p, c_i, c_p]),
     "bf_cholesky_fused": (c_i, [c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_p, c_p, c_p, c_i, c_p]),
     "bf_zscore_targets_batched": (c_i, [c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     "bf_fantasy_rows": (c_i, [c_i, c_i, c_p, c_p, c_p, c_ll, c_p, c_p, c_p, c_d, c_d, c_d, c_d, c_p, c_p, c_p, c_p]),

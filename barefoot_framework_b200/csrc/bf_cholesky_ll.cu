@@ -28,6 +28,21 @@
 #define BF_LL_CTAS_PER_SM 2
 #define BF_LL_MAX_NP 1024
 
+// Phase profile (tools/prof_chol_ll.cu builds with -DBF_LL_PROFILE): cycles of warp 0 (slots 0-6) and warp 1 (7-9)
+#ifdef BF_LL_PROFILE
+__device__ long long bf_ll_prof[16];
+#define LL_T0() long long ll_t_ = clock64()
+#define LL_MARK(slot)                                                                              \
+    do {                                                                                           \
+        const long long now_ = clock64();                                                          \
+        if ((threadIdx.x & 31) == 0) atomicAdd((unsigned long long*)&bf_ll_prof[slot], (unsigned long long)(now_ - ll_t_)); \
+        ll_t_ = now_;                                                                              \
+    } while (0)
+#else
+#define LL_T0()
+#define LL_MARK(slot)
+#endif
+
 struct LLParams {
     int kern, n, d, np, nb;
     const double *X, *inv_l2, *amp, *yerr;
@@ -66,15 +81,27 @@ __device__ __forceinline__ void ll_accumulate(double (&c)[4][4][2], const double
                     rb[(s + 1) % BF_LL_RING][t] = *reinterpret_cast<const double2*>(Bj + (size_t)(8 * t) * np + 8 * gn);
                 }
             }
+            // 16 independent accumulators per k-step: never two DMMAs on the same accumulator back to back
 #pragma unroll
             for (int t = 0; t < 4; ++t)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    bf_dmma(c[t][u][0], c[t][u][1], ra[s][t].x, rb[s][u].x);
-                    bf_dmma(c[t][u][0], c[t][u][1], ra[s][t].y, rb[s][u].y);
-                }
+                for (int u = 0; u < 4; ++u) bf_dmma(c[t][u][0], c[t][u][1], ra[s][t].x, rb[s][u].x);
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) bf_dmma(c[t][u][0], c[t][u][1], ra[s][t].y, rb[s][u].y);
         }
     }
+}
+
+// Pull rows [32 ib, 32 ib + 32) x columns [0, ncols) of the factor into L2 ahead of the register ring: with three
+// hundred sets in flight the finished blocks of a set have left the L2 by the time they are needed again, and a
+// one-group register ring cannot cover HBM latency.  One bulk prefetch per lane (= per row), no registers held.
+__device__ __forceinline__ void ll_prefetch_rows(const double* __restrict__ A, int np, int ib, int ncols) {
+    if (ncols <= 0) return;
+    const int lane = threadIdx.x & 31;
+    const double* row = A + (size_t)(32 * ib + lane) * np;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"(ncols * 8) : "memory");
 }
 
 __device__ __forceinline__ void ll_zero(double (&c)[4][4][2]) {
@@ -86,38 +113,110 @@ __device__ __forceinline__ void ll_zero(double (&c)[4][4][2]) {
 
 // c <- K[i-block, j-block] - c, K generated from the pre-scaled coordinates in shared memory
 // (xs[a * np + row]); identity padding beyond n; the noise of george's compute() on the diagonal.
+// D > 0: nDim known at compile time - the lane's 4 row points stay in registers and the 8 elements of a column
+// atom (4 rows x 2 columns) are independent evaluation chains (the FP64 pipe, not latency, is then the limit);
+// D == 0: run-time nDim (9..16), coordinates re-read from shared memory.
+template <int D>
 __device__ __forceinline__ void ll_kernel_tile(double (&c)[4][4][2], const LLParams& p, const double* __restrict__ xs,
                                                const double* __restrict__ tab, double amp,
                                                const double* __restrict__ yerr, int ib, int jb) {
+    constexpr int DR = D ? D : 1;
+    const int dd = D ? D : p.d;
     const int lane = threadIdx.x & 31, r = lane >> 2, q = lane & 3;
+    const int np = p.np, n = p.n, kern = p.kern;
+    double xr[4][DR];
+    if (D) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int a = 0; a < DR; ++a) xr[t][a] = xs[a * np + 32 * ib + 8 * t + r];
+    }
+    // all 32 squared distances of the lane first, then 32 independent radial evaluations: a lone warp per
+    // scheduler has nothing else to hide the FP64 latency with
+    double qq[4][4][2];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
+        const int col0 = 32 * jb + 8 * u + 2 * q;
+        if (D) {
+            double xc[2][DR];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int col = 32 * jb + 8 * u + 2 * q + e;
+            for (int e = 0; e < 2; ++e)
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int row = 32 * ib + 8 * t + r;
-                double v;
-                if (row < p.n && col < p.n) {
-                    double qq = 0.0;
-                    for (int a = 0; a < p.d; ++a) {
-                        const double df = xs[a * p.np + row] - xs[a * p.np + col];
-                        qq = fma(df, df, qq);
+                for (int a = 0; a < DR; ++a) xc[e][a] = xs[a * np + col0 + e];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int a = 0; a < DR; ++a) {
+                        const double df = xr[t][a] - xc[e][a];
+                        s = fma(df, df, s);
                     }
-                    v = amp * bf_radial_q(p.kern, qq, tab);
-                    if (row == col) {
-                        const double er = p.yerr_n == 1 ? yerr[0] : yerr[row];
-                        const double s = sqrt(er * er + BF_TINY);      // george folds the jitter into yerr
-                        v += s * s;
-                    }
-                } else {
-                    v = (row == col) ? 1.0 : 0.0;
+                    qq[t][u][e] = s;
                 }
-                c[t][u][e] = v - c[t][u][e];
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) qq[t][u][e] = 0.0;
+            for (int a = 0; a < dd; ++a) {
+                const double x0 = xs[a * np + col0], x1 = xs[a * np + col0 + 1];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const double xrow = xs[a * np + 32 * ib + 8 * t + r];
+                    const double d0 = xrow - x0, d1 = xrow - x1;
+                    qq[t][u][0] = fma(d0, d0, qq[t][u][0]);
+                    qq[t][u][1] = fma(d1, d1, qq[t][u][1]);
+                }
             }
         }
     }
+    const bool interior = 32 * ib + 31 < n && 32 * jb + 31 < n && ib != jb;
+    if (interior) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) c[t][u][e] = amp * bf_radial_q(kern, qq[t][u][e], tab) - c[t][u][e];
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int row = 32 * ib + 8 * t + r, col = 32 * jb + 8 * u + 2 * q + e;
+                    double v = amp * bf_radial_q(kern, qq[t][u][e], tab);
+                    if (row >= n || col >= n) v = (row == col) ? 1.0 : 0.0;
+                    else if (row == col) {
+                        const double er = p.yerr_n == 1 ? yerr[0] : yerr[row];
+                        const double sd = sqrt(er * er + BF_TINY);          // george folds the jitter into yerr
+                        v += sd * sd;
+                    }
+                    c[t][u][e] = v - c[t][u][e];
+                }
+    }
+}
+
+// c <- K[i-block, j-block] - c with K read from the factor buffer itself (in place: every tile of K is read exactly
+// once, right before the same warp overwrites it with the finished block of L)
+__device__ __forceinline__ void ll_load_tile(double (&c)[4][4][2], const double* __restrict__ A, int np, int ib, int jb) {
+    const int lane = threadIdx.x & 31, r = lane >> 2, q = lane & 3;
+    const double* src = A + (size_t)(32 * ib + r) * np + 32 * jb + 2 * q;
+    double2 k[4][4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) k[t][u] = *reinterpret_cast<const double2*>(src + (size_t)(8 * t) * np + 8 * u);
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            c[t][u][0] = k[t][u].x - c[t][u][0];
+            c[t][u][1] = k[t][u].y - c[t][u][1];
+        }
 }
 
 // P = C L_jj^-T for a tile below the diagonal, stored as L[ib, jb]: the accumulators become the DMMA A operand
@@ -152,6 +251,7 @@ __device__ __forceinline__ void ll_solve_store(double (&c)[4][4][2], const doubl
             *reinterpret_cast<double2*>(dst + (size_t)(8 * t) * np + 8 * u) = make_double2(pacc[t][u][0], pacc[t][u][1]);
 }
 
+template <int D, bool GEN>
 __global__ void __launch_bounds__(BF_LL_THREADS, BF_LL_CTAS_PER_SM) bf_cholesky_ll_kernel(LLParams p) {
     extern __shared__ __align__(16) double ll_sm[];
     double* xs = ll_sm;                                             // d x np, pre-scaled by the metric
@@ -162,20 +262,22 @@ __global__ void __launch_bounds__(BF_LL_THREADS, BF_LL_CTAS_PER_SM) bf_cholesky_
     __shared__ double w_s[BF_MAX_DIM];
     __shared__ int bad;
     const int set = blockIdx.x;
-    const int hp = p.set_hp ? p.set_hp[set] : set;
+    const int hp = (GEN && p.set_hp) ? p.set_hp[set] : set;
     const int np = p.np, nb = p.nb;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, q = lane & 3;
     double* A = p.L + (size_t)set * np * np;
-    const double* yerr = p.yerr + (p.yerr_n == 1 ? 0 : (size_t)set * p.yerr_stride);
-    const double amp = p.amp[hp];
+    const double* yerr = GEN ? p.yerr + (p.yerr_n == 1 ? 0 : (size_t)set * p.yerr_stride) : nullptr;
+    const double amp = GEN ? p.amp[hp] : 0.0;
 
     if (threadIdx.x == 0) bad = 0;
-    if (threadIdx.x < p.d) w_s[threadIdx.x] = bf_metric_scale(p.kern, p.inv_l2[(size_t)hp * p.d + threadIdx.x]);
+    if (GEN && threadIdx.x < p.d) w_s[threadIdx.x] = bf_metric_scale(p.kern, p.inv_l2[(size_t)hp * p.d + threadIdx.x]);
     if (threadIdx.x < BF_EXP_TAB_N) tab[threadIdx.x] = bf_exp_tab_g[threadIdx.x];
     __syncthreads();
-    for (int e = threadIdx.x; e < np * p.d; e += BF_LL_THREADS) {
-        const int i = e / p.d, a = e - i * p.d;
-        xs[a * np + i] = i < p.n ? p.X[(size_t)i * p.d + a] * w_s[a] : 0.0;
+    if (GEN) {
+        for (int e = threadIdx.x; e < np * p.d; e += BF_LL_THREADS) {
+            const int i = e / p.d, a = e - i * p.d;
+            xs[a * np + i] = i < p.n ? p.X[(size_t)i * p.d + a] * w_s[a] : 0.0;
+        }
     }
     __syncthreads();
 
@@ -185,8 +287,11 @@ __global__ void __launch_bounds__(BF_LL_THREADS, BF_LL_CTAS_PER_SM) bf_cholesky_
         double c[4][4][2];
         ll_zero(c);
         const double* Bd = A + (size_t)(32 * jd + r) * np + 2 * q;
+        LL_T0();
         ll_accumulate(c, Bd, Bd, np, 4 * jd);
-        ll_kernel_tile(c, p, xs, tab, amp, yerr, jd, jd);
+        LL_MARK(3);
+        if (GEN) ll_kernel_tile<D>(c, p, xs, tab, amp, yerr, jd, jd); else ll_load_tile(c, A, np, jd, jd);
+        LL_MARK(1);
 #pragma unroll
         for (int t = 0; t < 4; ++t)
 #pragma unroll
@@ -196,11 +301,13 @@ __global__ void __launch_bounds__(BF_LL_THREADS, BF_LL_CTAS_PER_SM) bf_cholesky_
             }
         __syncwarp();
         const int b = rl_factor_block(Ld, rdiag, lane);
+        LL_MARK(4);
         if (b && lane == 0 && bad == 0) bad = 32 * jd + b;
 #pragma unroll 8
         for (int jj = 0; jj < 32; ++jj) A[(size_t)(32 * jd + jj) * np + 32 * jd + lane] = Ld[jj][lane];
         double (*Li)[33] = Li0 + 32 * (jd & 1);
         rl_invert_block(Ld, rdiag, Li, lane);
+        LL_MARK(5);
         if (p.dinv) {
             double* dv = p.dinv + ((size_t)set * nb + jd) * 1024;
 #pragma unroll 8
@@ -220,22 +327,42 @@ __global__ void __launch_bounds__(BF_LL_THREADS, BF_LL_CTAS_PER_SM) bf_cholesky_
             if (j + 1 < nb) {
                 double c[4][4][2];
                 ll_zero(c);
+                if (j + 2 < nb) ll_prefetch_rows(A, np, j + 2, 32 * j);     // next column's look-ahead tile (its last block comes later)
+                LL_T0();
                 ll_accumulate(c, A + (size_t)(32 * (j + 1) + r) * np + 2 * q, Bj, np, 4 * j);
-                ll_kernel_tile(c, p, xs, tab, amp, yerr, j + 1, j);
+                LL_MARK(0);
+                if (GEN) ll_kernel_tile<D>(c, p, xs, tab, amp, yerr, j + 1, j); else ll_load_tile(c, A, np, j + 1, j);
+                LL_MARK(1);
                 ll_solve_store(c, Li, A, np, j + 1, j);
+                LL_MARK(2);
                 __syncwarp();                   // the tile just stored is read back by the other lanes below
                 diagonal(j + 1);
             }
+            {
+                LL_T0();
+                __syncthreads();
+                LL_MARK(6);
+            }
+            continue;
         } else {
+            LL_T0();
             for (int i = j + 1 + warp; i < nb; i += BF_LL_WARPS - 1) {
                 double c[4][4][2];
                 ll_zero(c);
+                // the rows of this warp's next tile: of this column, or its first one of the next column
+                const int inext = i + BF_LL_WARPS - 1 < nb ? i + BF_LL_WARPS - 1 : j + 2 + warp;
+                if (inext < nb) ll_prefetch_rows(A, np, inext, 32 * j);
                 ll_accumulate(c, A + (size_t)(32 * i + r) * np + 2 * q, Bj, np, 4 * j);
-                ll_kernel_tile(c, p, xs, tab, amp, yerr, i, j);
+                if (GEN) ll_kernel_tile<D>(c, p, xs, tab, amp, yerr, i, j); else ll_load_tile(c, A, np, i, j);
                 ll_solve_store(c, Li, A, np, i, j);
             }
+            if (warp == 1) LL_MARK(7);
         }
-        __syncthreads();                        // column j of L complete and visible; L_{j+1,j+1}^-1 ready
+        {
+            LL_T0();
+            __syncthreads();                    // column j of L complete and visible; L_{j+1,j+1}^-1 ready
+            if (warp == 1) LL_MARK(8);
+        }
     }
     if (p.zero_upper) {                         // dense consumers (keep_dense): zeros in the blocks above the diagonal
         for (int e = threadIdx.x; e < np * (np / 2); e += BF_LL_THREADS) {
@@ -247,6 +374,36 @@ __global__ void __launch_bounds__(BF_LL_THREADS, BF_LL_CTAS_PER_SM) bf_cholesky_
 }
 
 static size_t ll_smem_bytes(int np, int d) { return sizeof(double) * ((size_t)d * np + BF_EXP_TAB_N + 3 * 32 * 33); }
+
+template <int D, bool GEN>
+static int ll_launch(const LLParams& p, int S, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(bf_cholesky_ll_kernel<D, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        bf_set_error("bf_cholesky_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    bf_cholesky_ll_kernel<D, GEN><<<S, BF_LL_THREADS, smem, st>>>(p);
+    return 0;
+}
+
+// In-place variant: L holds K (lower blocks, bf_kernel_matrix_lower) on entry.
+extern "C" int bf_cholesky_ll_inplace(int n, int S, double* K_inout_L, int32_t* info, double* dinv, int zero_upper,
+                                      void* stream) {
+    BF_CHECK_ARG(n > 0 && S >= 0 && K_inout_L, BF_ERR_ARG, "bf_cholesky_ll_inplace: bad argument");
+    BF_CHECK_ARG(bf_padded_n(n) <= BF_LL_MAX_NP, BF_ERR_SIZE, "bf_cholesky_ll_inplace: n=%d too large", n);
+    BF_CHECK_ARG(((uintptr_t)K_inout_L & 15) == 0, BF_ERR_ALIGN, "bf_cholesky_ll_inplace: buffer must be 16-byte aligned");
+    if (S == 0) return 0;
+    LLParams p;
+    p.kern = 0; p.n = n; p.d = 1; p.np = bf_padded_n(n); p.nb = p.np / 32;
+    p.X = nullptr; p.inv_l2 = nullptr; p.amp = nullptr; p.yerr = nullptr; p.set_hp = nullptr;
+    p.yerr_n = 1; p.yerr_stride = 0;
+    p.L = K_inout_L; p.info = info; p.dinv = dinv; p.zero_upper = zero_upper;
+    const size_t smem = ll_smem_bytes(p.np, 1);      // the (unused) coordinate area keeps the carve-up of the generating variant
+    int rc = ll_launch<1, false>(p, S, smem, (cudaStream_t)stream);
+    if (rc) return rc;
+    BF_CHECK_LAUNCH("bf_cholesky_ll_inplace");
+    return 0;
+}
 
 extern "C" int bf_cholesky_fused_supported(int n, int d) {
     const int np = bf_padded_n(n);
@@ -270,12 +427,14 @@ extern "C" int bf_cholesky_fused(int kern, int n, int d, int S, const double* X,
     p.yerr_n = yerr_n; p.yerr_stride = yerr_stride;
     p.L = L; p.info = info; p.dinv = dinv; p.zero_upper = zero_upper;
     const size_t smem = ll_smem_bytes(p.np, d);
-    cudaError_t e = cudaFuncSetAttribute(bf_cholesky_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-        bf_set_error("bf_cholesky_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        return (int)e;
+    int rc = 0;
+    switch (d) {
+#define BF_CASE(DD) case DD: rc = ll_launch<DD, true>(p, S, smem, (cudaStream_t)stream); break;
+        BF_CASE(1) BF_CASE(2) BF_CASE(3) BF_CASE(4) BF_CASE(5) BF_CASE(6) BF_CASE(7) BF_CASE(8)
+#undef BF_CASE
+        default: rc = ll_launch<0, true>(p, S, smem, (cudaStream_t)stream); break;      // nDim 9..16 at run time
     }
-    bf_cholesky_ll_kernel<<<S, BF_LL_THREADS, smem, (cudaStream_t)stream>>>(p);
+    if (rc) return rc;
     BF_CHECK_LAUNCH("bf_cholesky_fused");
     return 0;
 }

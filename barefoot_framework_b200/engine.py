@@ -102,11 +102,14 @@ def section_ms(name):
     return sum(a.elapsed_time(b) for nm, a, b in (timeline or []) if nm == name)
 
 
-# Factorisation kernel choice: "auto" = the fused left-looking kernel (bf_cholesky_fused: kernel tiles generated
-# into the accumulators, no K in HBM, several sets per SM) for many sets, the right-looking shared-memory-panel
-# kernel (bf_kernel_matrix_lower + bf_cholesky_batched) for a few; "ll" / "rl" force one (measurements, tests).
-CHOLESKY = "auto"
-FUSED_MIN_SETS = 32
+# Factorisation kernel choice.  "rl" (default) = bf_kernel_matrix_lower + the right-looking shared-memory-panel
+# kernel bf_cholesky_batched; "ll" = the fused left-looking kernel bf_cholesky_fused (kernel tiles generated into
+# the accumulators, no K in HBM, two sets per SM).  Measured on B200 at n = 500, S = 1000 (tools/bench_setup.py,
+# tools/prof_chol_ll.cu, profiles/r2_cholesky_variants.json): rl 0.93 + 3.78 ms, ll 8.4 ms fused / 4.45 ms
+# in place - the left-looking form is bound by the single-warp chains of its diagonal warp (L2-latency-bound
+# accumulation through a two-slot ring + the 32 x 32 factorisation) and by FP64 kernel evaluation at 8 warps per
+# SM, so it stays an option (it also covers padded sizes up to 1024, the right-looking panel 736).
+CHOLESKY = "rl"
 POISON_SCRATCH = False      # tests: fill the factor scratch with NaN first (no consumer may read an unwritten block)
 
 
@@ -117,9 +120,7 @@ def _scratch(shape, dev):
 
 
 def _use_fused(n, d, S):
-    if CHOLESKY == "rl" or not _lib.load().bf_cholesky_fused_supported(int(n), int(d)):
-        return False
-    return CHOLESKY == "ll" or S >= FUSED_MIN_SETS
+    return CHOLESKY == "ll" and bool(_lib.load().bf_cholesky_fused_supported(int(n), int(d)))
 
 
 class GPFactors:

@@ -272,6 +272,10 @@ int bf_zscore_targets(int n, const double* f_mean, const double* f_var, double* 
  * untouched unless zero_upper is set.  info [S] as bf_cholesky_batched; dinv (optional) as
  * bf_cholesky_batched_dinv. */
 int bf_cholesky_fused_supported(int n, int d);
+/* The same left-looking factorisation on a buffer that already holds K in its lower blocks
+ * (bf_kernel_matrix_lower): in place, like bf_cholesky_batched(_dinv). */
+int bf_cholesky_ll_inplace(int n, int S, double* K_inout_L, int32_t* info, double* dinv, int zero_upper,
+                           void* stream);
 int bf_cholesky_fused(int kern, int n, int d, int S, const double* X, const double* inv_l2,
                       const double* amp, const int32_t* set_hp, const double* yerr, int yerr_n,
                       long long yerr_stride, double* L, int32_t* info, double* dinv, int zero_upper,

@@ -48,8 +48,18 @@ def main():
             alpha = torch.empty((S, n), dtype=torch.float64, device=dev)
             info = torch.zeros((S,), dtype=torch.int32, device=dev)
             st = stream()
-            t = {"kernel_matrix": [], "cholesky": [], "factor_finish": []}
+            t = {"kernel_matrix": [], "cholesky": [], "factor_finish": [], "cholesky_fused": []}
             for rep in range(args.reps + 1):
+                if lib.bf_cholesky_fused_supported(n, d):
+                    # the fused left-looking kernel (no K in memory) on the same inputs
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    call("bf_cholesky_fused", KERN[args.kernel], n, d, S, ptr(X), ptr(inv_l2), ptr(amp), None, ptr(yerr), n, n,
+                         ptr(K), ptr(info), None, 0, st)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    if rep:
+                        t["cholesky_fused"].append(e0.elapsed_time(e1))
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
                 ev[0].record()
                 call("bf_kernel_matrix_lower", KERN[args.kernel], n, d, S, ptr(X), ptr(inv_l2), ptr(amp), None,
@@ -65,8 +75,11 @@ def main():
                     t["cholesky"].append(ev[1].elapsed_time(ev[2]))
                     t["factor_finish"].append(ev[2].elapsed_time(ev[3]))
             assert int(info.max().item()) == 0
-            med = {k: float(np.median(v)) for k, v in t.items()}
-            tot = sum(med.values())
+            med = {k: float(np.median(v)) for k, v in t.items() if v}
+            tot = med["kernel_matrix"] + med["cholesky"] + med["factor_finish"]
+            if "cholesky_fused" in med:
+                med["fused_tflops_n3_over_3"] = S * (n ** 3 / 3.0) / (med["cholesky_fused"] * 1e-3) / 1e12
+                med["us_per_set_fused_plus_finish"] = 1e3 * (med["cholesky_fused"] + med["factor_finish"]) / S
             print(json.dumps({"n": n, "S": S, "d": d, "kernel": args.kernel, "ms": med, "ms_total": tot,
                               "us_per_set": 1e3 * tot / S, "sets_per_s": S / (tot * 1e-3),
                               "tflops_chol_plus_inverse": S * (2.0 * n ** 3 / 3.0) / (tot * 1e-3) / 1e12}), flush=True)
