@@ -198,3 +198,67 @@ def test_sampling_and_constraints_match_reference():
     np.testing.assert_array_equal(util.cartesian(np.linspace(0, 1, 3), np.linspace(0, 1, 4), np.array([0.5, 0.7])),
                                   g["cartesian"])
     np.testing.assert_array_equal(util.composition_sampler(4, 11), g["composition"])
+
+
+# ---- k-medoids oracle at sizes without the N x N matrix ------------------------------------------------------
+def _km_rows(N, f, seed):
+    rng = np.random.default_rng(seed)
+    cols = [np.exp(rng.normal(size=N)), rng.integers(0, 10 ** 6, size=N).astype(float),
+            rng.integers(0, 3, size=N).astype(float)]
+    return np.ascontiguousarray(np.column_stack(cols[:f]))
+
+
+def test_blocked_kmedoids_oracle_equals_the_full_matrix_shim_bit_for_bit():
+    """oracle/kmedoids_blocked.py (what generated tests/golden/kmedoids_full.npz at N' = 1e5) against
+    oracle/kmedoids_shim.py (full pairwise_distances matrix) on the reference's row shapes: same row sums,
+    medoids, labels and iteration count, serial and with forked cluster workers."""
+    from oracle import kmedoids_blocked as kb
+    from oracle.kmedoids_shim import KMedoids, pairwise_euclidean
+    for seed, (N, f, k) in enumerate([(1500, 3, 6), (1203, 2, 5), (257, 3, 4)]):
+        X = _km_rows(N, f, seed)
+        D = pairwise_euclidean(X)
+        assert np.array_equal(D.sum(axis=1), kb.row_sums(X, block=256))
+        km = KMedoids(n_clusters=k, random_state=0).fit(X)
+        for workers in (1, 3):
+            med, lab, it = kb.fit(X, k, workers=workers)
+            assert np.array_equal(med, km.medoid_indices_) and np.array_equal(lab, km.labels_) and it == km.n_iter_
+    assert np.array_equal(kb.kmedoids_max(_km_rows(300, 3, 9), 4), fast.kmedoids_max(_km_rows(300, 3, 9), 4)[0])
+
+
+def test_full_size_kmedoids_golden_is_self_consistent():
+    """tests/golden/kmedoids_full.npz: the stored inputs checksum, one medoid per cluster, labels are the first
+    arg-min over the stored medoids (expanded-form distances from scikit-learn)."""
+    import os
+    from conftest import GOLDEN, golden
+    from oracle import kmedoids_blocked as kb
+    from sklearn.utils.extmath import row_norms
+    if not os.path.isfile(os.path.join(GOLDEN, "kmedoids_full.npz")):
+        pytest.skip("not generated")
+    g = golden("kmedoids_full.npz")
+    for f in (3, 2):
+        X = _km_rows(int(g["N"]), f, int(g["seed"]))
+        np.testing.assert_array_equal(np.array([X.sum(), (X * np.arange(1, f + 1)).sum()]), g["f%d_x_checksum" % f])
+        med = g["f%d_medoids" % f]
+        assert len(set(med.tolist())) == int(g["k"]) and int(g["f%d_n_iter" % f]) < 300
+        labels = kb.labels_of(X, row_norms(X, squared=True), med)
+        np.testing.assert_array_equal(labels, g["f%d_labels" % f].astype(np.int64))
+
+
+def test_expanded_distance_form_is_not_symmetric_and_breaks_exact_ties_by_rounding():
+    """Why a selection of the reference can be irreproducible: scikit-learn's distances are
+    (-2 x.y + |x|^2) + |y|^2, so D[a, b] and D[b, a] may differ in the last bit.  In a cluster of exactly two points
+    the two candidate medoids have costs D[b, a] and D[a, b] - an exact tie in real arithmetic - and the alternate
+    loop moves the medoid iff the other one is STRICTLY cheaper, i.e. on that last bit.  A relative change of
+    1e-13 in the values (the accuracy any second implementation of the acquisition has) flips it for some pairs."""
+    from oracle.kmedoids_shim import pairwise_euclidean
+    rng = np.random.default_rng(0)
+    asym = flips = 0
+    for _ in range(400):
+        X = np.column_stack([rng.uniform(0.5, 3.0, size=2), rng.integers(0, 30, size=2).astype(float), [2.0, 2.0]])
+        D = pairwise_euclidean(X)
+        asym += D[0, 1] != D[1, 0]
+        Xp = X.copy()
+        Xp[:, 0] *= 1 + 1e-13
+        Dp = pairwise_euclidean(Xp)
+        flips += np.sign(D[0, 1] - D[1, 0]) != np.sign(Dp[0, 1] - Dp[1, 0])
+    assert asym > 0 and flips > 0

@@ -73,10 +73,18 @@ CASES = [
      dict(covFunc="M52", iterLimit=2, sampleCount=6, hpCount=8, batchSize=2, tmIter=1, fusedPoints=10,
           fusedSamples=60, lowBound=0.05), 4),
     # a mid-size run: 3 x 30 x 60 = 5400 ROM-stage work items (the few-candidates solve path, chunked),
-    # 60 sets x 500 candidates in the TM stage, k-medoids over the clustered rows
+    # 60 sets x 500 candidates in the TM stage, k-medoids over the clustered rows.  Seeds 15 and 25: with seed 5
+    # (round 1) iteration 1 clusters 9 rows into 4 clusters two of which hold exactly TWO points; the two
+    # candidate medoids of such a cluster tie exactly (cost = their mutual distance) and scikit-learn's expanded
+    # distance form breaks the tie by the last bit of (-2 x.y + |x|^2) + |y|^2 versus (-2 x.y + |y|^2) + |x|^2,
+    # i.e. by rounding noise that a 1e-13 relative change of the acquisition values flips: the reference's own
+    # selection is then not reproducible by any second implementation (tests/test_oracle_golden.py shows it).
     ("mid_se_kg", dict(reification=True, acquisitionFunc="KG", tmSampleOpt="KG", initDataPathorNum=[5, 5, 5, 5]),
      dict(covFunc="SE", iterLimit=2, sampleCount=30, hpCount=60, batchSize=4, tmIter=1, fusedPoints=60,
-          fusedSamples=500, lowBound=0.05), 5),
+          fusedSamples=500, lowBound=0.05), 15),
+    ("mid_se_kg_s25", dict(reification=True, acquisitionFunc="KG", tmSampleOpt="KG", initDataPathorNum=[5, 5, 5, 5]),
+     dict(covFunc="SE", iterLimit=2, sampleCount=30, hpCount=60, batchSize=4, tmIter=1, fusedPoints=60,
+          fusedSamples=500, lowBound=0.05), 25),
     ("batch_only_ei", dict(reification=False, acquisitionFunc="EI", tmSampleOpt="EI", initDataPathorNum=[4]),
      dict(covFunc="M32", iterLimit=3, sampleCount=30, hpCount=25, batchSize=3, tmIter=5, fusedPoints=10,
           fusedHP=[3, 0.1, 0.1]), 3),
