@@ -48,7 +48,8 @@ SIGNATURES = {
     "bf_top2": (c_i, [c_ll, c_i, c_p, c_p, c_p, c_p]),
     "bf_kg_diag": (c_i, [c_ll, c_ll, c_i, c_p, c_p, c_p, c_p, c_d, c_p, c_p, c_p, c_p, c_p, c_p]),
     "bf_kg_full_max_n": (c_i, []),
-    "bf_kg_full": (c_i, [c_i, c_ll, c_i, c_p, c_p, c_d, c_p, c_p, c_p, c_p]),
+    "bf_kg_full_workspace": (c_sz, [c_i, c_ll, c_i]),
+    "bf_kg_full": (c_i, [c_i, c_ll, c_i, c_p, c_p, c_d, c_p, c_p, c_p, c_p, c_p]),
     "bf_acq_tiles": (c_i, [c_ll]),
     "bf_acq_eval": (c_i, [c_i, c_ll, c_i, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_p]),
     "bf_reification": (c_i, [c_i, c_ll, c_p, c_p, c_p, c_p, c_p]),

@@ -206,6 +206,9 @@ def build_factors(kern, X, y, l_sq, sigma_f, yerr, ndim=None, set_hp=None, n_set
     f = GPFactors(kern, X, inv_l2, amp, hp_t, linv_packed, alpha, S,
                   L=Lbuf if keep_dense else None, Linv=Libuf if keep_dense else None)
     f.info = info
+    # host copies of the small per-set scalars, so per-set launches (predict_cov) never read the device back
+    f.amp_host = np.atleast_1d(amplitude(sigma_f, ndim)).astype(np.float64)
+    f.set_hp_host = None if set_hp is None else np.asarray(set_hp, dtype=np.int64)
     if check:
         f.raise_if_not_positive_definite()
     return f
@@ -387,23 +390,28 @@ def solve_rows(f, Xa, set_index=0, want_mean=True):
     Ks = torch.empty((Ap, np_), dtype=F64, device=Xa.device)
     Vt = torch.empty((Ap, np_), dtype=F64, device=Xa.device)
     mean = torch.empty((A,), dtype=F64, device=Xa.device) if want_mean else None
-    hp = int(f.set_hp[set_index].item()) if f.set_hp is not None else set_index
-    amp = float(f.amp[hp].item())
+    hp_host = getattr(f, "set_hp_host", None)
+    if f.set_hp is None:
+        hp = set_index
+    else:
+        hp = int(hp_host[set_index]) if hp_host is not None else int(f.set_hp[set_index].item())
+    amp_host = getattr(f, "amp_host", None)
+    amp = float(amp_host[hp]) if amp_host is not None else float(f.amp[hp].item())
     call("bf_gp_solve_rows", KERN[f.kern], A, f.n, f.d, ptr(Xa), ptr(f.X), f.inv_l2[hp].data_ptr(), amp,
          f.Linv[set_index].data_ptr(), f.alpha[set_index].data_ptr(), ptr(Ks), ptr(Vt), ptr(mean), stream())
     return Xa, Vt, mean, hp, amp
 
 
-def posterior_cov(f, Xa, Xb=None, set_index=0):
+def posterior_cov(f, Xa, Xb=None, set_index=0, out=None):
     """gp_model.predict_cov (gpModel.py:44-48): posterior mean at Xa and the full covariance
-    between Xa and Xb (default Xb = Xa) for one set."""
+    between Xa and Xb (default Xb = Xa) for one set (written into `out` [A, B] when given)."""
     Xa, Vta, mean, hp, amp = solve_rows(f, Xa, set_index)
     if Xb is None:
         Xb, Vtb = Xa, Vta
     else:
         Xb, Vtb, _, _, _ = solve_rows(f, Xb, set_index, want_mean=False)
     A, B = Xa.shape[0], Xb.shape[0]
-    C = torch.empty((A, B), dtype=F64, device=Xa.device)
+    C = torch.empty((A, B), dtype=F64, device=Xa.device) if out is None else out
     call("bf_gp_cov", KERN[f.kern], A, B, f.n, f.d, ptr(Xa), ptr(Xb), f.inv_l2[hp].data_ptr(), amp,
          ptr(Vta), ptr(Vtb), ptr(C), B, stream())
     return mean, C
@@ -411,7 +419,8 @@ def posterior_cov(f, Xa, Xb=None, set_index=0):
 
 def kg_full(mu, sigma, M=None, sn=SN_KG):
     """knowledge_gradient(M, sn, mu, sigma) with a dense covariance (acquisitionFunc.py:12-96):
-    mu [N] or [S, N], sigma [N, N] or [S, N, N].  Returns device tensors (kg_val [S], kg_idx [S], nu [S, M])."""
+    mu [N] or [S, N], sigma [N, N] or [S, N, N]; ONE launch for all S sets.  N <= 4096 sorts in shared memory,
+    larger N (to 65536) on a device scratch.  Returns device tensors (kg_val [S], kg_idx [S], nu [S, M])."""
     mu = to_dev(mu)
     mu2 = mu.reshape(1, -1) if mu.dim() == 1 else mu
     S, N = mu2.shape
@@ -421,25 +430,36 @@ def kg_full(mu, sigma, M=None, sn=SN_KG):
     kg_val = torch.empty((S,), dtype=F64, device=mu2.device)
     kg_idx = torch.empty((S,), dtype=torch.int64, device=mu2.device)
     st = stream()
+    lib = _lib.load()
     for s0 in range(0, S, 65535):
         sc = min(65535, S - s0)
+        nbytes = lib.bf_kg_full_workspace(N, M, sc)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=mu2.device) if nbytes else None
         call("bf_kg_full", N, M, sc, mu2[s0:].data_ptr(), sg[s0:].data_ptr(), float(sn), nu[s0:].data_ptr(),
-             kg_val[s0:].data_ptr(), kg_idx[s0:].data_ptr(), st)
+             kg_val[s0:].data_ptr(), kg_idx[s0:].data_ptr(), ptr(ws), st)
     return kg_val, kg_idx, nu[:, :M]
 
 
-def kg_full_from_factors(f, x_test, shift=0.0, sn=SN_KG):
-    """Batch-only KG (util.py:952,1078-1081): per set, the full posterior covariance at x_test
-    (predict_cov) followed by the dense knowledge gradient.  Returns host arrays (values [S], indices [S])."""
+def kg_full_from_factors(f, x_test, shift=0.0, sn=SN_KG, max_bytes=8 << 30):
+    """Batch-only KG (util.py:952,1078-1081): the full posterior covariance at x_test (predict_cov) of every set,
+    then the dense knowledge gradient - the covariances of a chunk of sets (at most max_bytes) are built by
+    per-set launches without any host read-back and scored by ONE bf_kg_full launch.  Returns host arrays
+    (values [S], indices [S])."""
     xs = to_dev(x_test).reshape(len(x_test), -1)
-    vals, idxs = np.empty(f.S), np.empty(f.S, dtype=np.int64)
-    for s in range(f.S):
-        mean, cov = posterior_cov(f, xs, set_index=s)
-        if shift:
-            mean = mean + float(shift)
-        v, i, _ = kg_full(mean, cov, sn=sn)
-        vals[s], idxs[s] = float(v[0].item()), int(i[0].item())
-    return vals, idxs
+    N = xs.shape[0]
+    per_chunk = max(1, min(f.S, int(max_bytes // max(1, 8 * N * N))))
+    vals, idxs = [], []
+    for s0 in range(0, f.S, per_chunk):
+        sc = min(per_chunk, f.S - s0)
+        means = torch.empty((sc, N), dtype=F64, device=xs.device)
+        covs = torch.empty((sc, N, N), dtype=F64, device=xs.device)
+        for s in range(sc):
+            mean, _ = posterior_cov(f, xs, set_index=s0 + s, out=covs[s])
+            means[s] = mean if not shift else mean + float(shift)
+        v, i, _ = kg_full(means, covs, sn=sn)
+        vals.append(v)
+        idxs.append(i)
+    return torch.cat(vals).cpu().numpy(), torch.cat(idxs).cpu().numpy()
 
 
 def kg_from_sweep(res, M=None, sn=SN_KG, want_nu=False):

@@ -190,10 +190,16 @@ int bf_acq_eval(int kind, long long N, int S, const double* y, const double* spr
 /* mu [S x N], sigma [S x N x N] (column i of sigma is read for candidate i, as the reference does),
  * candidates i < M scored.  nu_out [S x M] receives every log-KG value; kg_val / kg_idx [S] the
  * running maximum from the reference's floor (0, 0).  N <= BF_KG_FULL_MAX_N. */
+/* N <= BF_KG_FULL_MAX_N: the lines of a candidate are sorted in shared memory (one CTA per candidate and set).
+ * Larger N (up to BF_KG_FULL_BIG_MAX_N): the same algorithm on a per-CTA scratch slice in device memory with a
+ * persistent grid over all (candidate, set) items; `workspace` must then hold bf_kg_full_workspace(N, M, S) bytes
+ * (it may be NULL otherwise).  Either way ONE call covers all S sets. */
 #define BF_KG_FULL_MAX_N 4096
+#define BF_KG_FULL_BIG_MAX_N 65536
 int bf_kg_full_max_n(void);
+size_t bf_kg_full_workspace(int N, long long M, int S);
 int bf_kg_full(int N, long long M, int S, const double* mu, const double* sigma, double sn,
-               double* nu_out, double* kg_val, long long* kg_idx, void* stream);
+               double* nu_out, double* kg_val, long long* kg_idx, void* workspace, void* stream);
 
 /* ---- (3) reification: reificationFusion.py:26-57 ------------------------------------------- */
 /* y, var: [m x P] (model-major).  mean_f, var_f: [P].  pinv semantics of numpy (rcond 1e-15). */

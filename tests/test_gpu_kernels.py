@@ -641,3 +641,49 @@ def test_fused_cholesky_solve_path_never_reads_unwritten_blocks(chol_mode):
     bad[S - 2, 0] = np.nan
     with pytest.raises(np.linalg.LinAlgError):
         eng.build_factors("M52", X, Y, bad ** 2, sf, YE)
+
+
+# ---- dense-covariance knowledge gradient beyond the shared-memory size (bf_kg_full, N > 4096) -------------------
+@pytest.mark.parametrize("N,S,M", [(4100, 2, 24), (9000, 2, 16), (16384, 1, 12)])
+def test_kg_full_large_n_matches_oracle(eng, N, S, M):
+    """The scratch-memory variant of the dense knowledge gradient (hybrid bitonic sort, same unique / Algorithm 1 /
+    summation as the shared-memory kernel) against oracle/fast.kg_full on the first M candidates of S sets in ONE
+    launch: correlated columns, duplicated candidates (equal slopes -> unique-with-max), large variances so that
+    values above the reference's floor occur."""
+    rng = np.random.default_rng(N + S)
+    mus, sigmas = [], []
+    for s_ in range(S):
+        B = rng.normal(size=(N, 24))
+        B[7] = B[3]                                   # duplicated candidates: identical covariance rows / columns
+        B[N - 5] = B[11]
+        sigma = (30.0 if s_ == 0 else 1.0) * (B @ B.T) / 24 + 1e-3 * np.eye(N)
+        mu = rng.normal(size=N)
+        mu[7] = mu[3] + 0.25
+        mus.append(mu)
+        sigmas.append(sigma)
+    v, i, nu = eng.kg_full(np.array(mus), np.array(sigmas), M=M)
+    v, i, nu = v.cpu().numpy(), i.cpu().numpy(), nu.cpu().numpy()
+    for s_ in range(S):
+        rv, ri, rnu = fast.kg_full(mus[s_], sigmas[s_], 0.1, M)
+        assert ri == int(i[s_]) and abs(rv - v[s_]) <= REL * max(1.0, abs(rv))
+        fin = np.isfinite(rnu)
+        assert np.array_equal(np.isfinite(nu[s_]), fin)
+        assert np.abs(nu[s_][fin] - rnu[fin]).max(initial=0) <= REL * np.abs(rnu[fin]).max(initial=1.0)
+
+
+def test_kg_full_scratch_and_shared_memory_kernels_agree_bit_for_bit(eng):
+    """The same 4096 lines through both kernels: N = 4096 runs in shared memory; padding the problem with one
+    candidate that can never be on the envelope (N = 4097 -> scratch kernel) must leave the other values unchanged."""
+    rng = np.random.default_rng(3)
+    N, M = 4096, 40
+    B = rng.normal(size=(N, 16))
+    sigma = 20.0 * (B @ B.T) / 16 + 1e-3 * np.eye(N)
+    mu = rng.normal(size=N)
+    _, _, nu_small = eng.kg_full(mu, sigma, M=M)
+    sigma2 = np.zeros((N + 1, N + 1))
+    sigma2[:N, :N] = sigma
+    sigma2[N, N] = 1.0                                 # an uncorrelated candidate: slope 0 for the first M columns ...
+    mu2 = np.append(mu, -1e6)                          # ... and an intercept below every other line
+    _, _, nu_big = eng.kg_full(mu2, sigma2, M=M)
+    a, b = nu_small.cpu().numpy()[0], nu_big.cpu().numpy()[0]
+    np.testing.assert_allclose(b, a, rtol=1e-13, atol=0)
