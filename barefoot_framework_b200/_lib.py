@@ -52,6 +52,8 @@ SIGNATURES = {
     "bf_kg_full": (c_i, [c_i, c_ll, c_i, c_p, c_p, c_d, c_p, c_p, c_p, c_p, c_p]),
     "bf_acq_tiles": (c_i, [c_ll]),
     "bf_acq_eval": (c_i, [c_i, c_ll, c_i, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "bf_records_pack": (c_i, [c_i, c_p, c_p, c_ll, c_p, c_p]),
+    "bf_records_reduce": (c_i, [c_i, c_i, c_p, c_p, c_p, c_p]),
     "bf_reification": (c_i, [c_i, c_ll, c_p, c_p, c_p, c_p, c_p]),
     "bf_kmedoids_rowsum": (c_i, [c_ll, c_i, c_p, c_ll, c_ll, c_p, c_p]),
     "bf_kmedoids_assign": (c_i, [c_ll, c_i, c_i, c_p, c_p, c_p, c_p]),

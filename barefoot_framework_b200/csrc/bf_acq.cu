@@ -89,3 +89,45 @@ extern "C" int bf_acq_eval(int kind, long long N, int S, const double* y, const 
     BF_CHECK_LAUNCH("bf_acq_eval(finalize)");
     return 0;
 }
+
+// ---- candidate-sharded stages: the per-rank (value, local index) records around the all-gather ------------------
+// pack: out[0..S) = values, out[S..2S) = (index + offset) bit-cast to double - ONE buffer for ONE collective.
+__global__ void bf_records_pack_kernel(int S, const double* __restrict__ val, const long long* __restrict__ idx,
+                                       long long offset, double* __restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) {
+        out[s] = val[s];
+        out[S + s] = __longlong_as_double(idx[s] + offset);
+    }
+}
+
+// reduce: gathered [world x 2 x S] -> per set the largest value and, among equal values, the lowest GLOBAL index
+// (numpy's first arg-max over the concatenated candidate array, acquisitionFunc.py:135-138); NaN never wins.
+__global__ void bf_records_reduce_kernel(int world, int S, const double* __restrict__ gathered,
+                                         double* __restrict__ best_val, long long* __restrict__ best_idx) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    BfBest b = bf_best_init();
+    for (int r = 0; r < world; ++r) {
+        const double* rec = gathered + (size_t)r * 2 * S;
+        bf_best_take(b, rec[s], __double_as_longlong(rec[S + s]));
+    }
+    best_val[s] = b.v;
+    best_idx[s] = b.i;
+}
+
+extern "C" int bf_records_pack(int S, const double* val, const long long* idx, long long offset, double* out, void* stream) {
+    BF_CHECK_ARG(S >= 0 && val && idx && out, BF_ERR_ARG, "bf_records_pack: bad argument");
+    if (S == 0) return 0;
+    bf_records_pack_kernel<<<(S + 127) / 128, 128, 0, (cudaStream_t)stream>>>(S, val, idx, offset, out);
+    BF_CHECK_LAUNCH("bf_records_pack");
+    return 0;
+}
+
+extern "C" int bf_records_reduce(int world, int S, const double* gathered, double* best_val, long long* best_idx, void* stream) {
+    BF_CHECK_ARG(world > 0 && S >= 0 && gathered && best_val && best_idx, BF_ERR_ARG, "bf_records_reduce: bad argument");
+    if (S == 0) return 0;
+    bf_records_reduce_kernel<<<(S + 127) / 128, 128, 0, (cudaStream_t)stream>>>(world, S, gathered, best_val, best_idx);
+    BF_CHECK_LAUNCH("bf_records_reduce");
+    return 0;
+}

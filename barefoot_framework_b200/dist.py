@@ -143,20 +143,62 @@ def _gather_packed(*cols):
             for k, c in enumerate(cols)]
 
 
-def reduce_candidate_shards(values, indices, index_offset):
+class _ShardReduction:
+    """Handle of a candidate-shard reduction whose all-gather is still in flight (NCCL runs it on its own stream
+    after the producing kernels): result() makes the current stream wait for it and applies the first-index
+    maximum with one small kernel.  Lets the next step's set-up and sweep start behind the collective."""
+
+    def __init__(self, work, gathered, world_size, S, device):
+        self.work, self.gathered, self.world_size, self.S, self.device = work, gathered, world_size, S, device
+
+    def result(self):
+        from . import _lib
+        if self.work is not None:
+            self.work.wait()
+        best_val = torch.empty((self.S,), dtype=torch.float64, device=self.device)
+        best_idx = torch.empty((self.S,), dtype=torch.int64, device=self.device)
+        _lib.call("bf_records_reduce", self.world_size, self.S, self.gathered.data_ptr(), best_val.data_ptr(),
+                  best_idx.data_ptr(), _lib.stream())
+        return best_val, best_idx
+
+
+class _Ready:
+    def __init__(self, out):
+        self.out = out
+
+    def result(self):
+        return self.out
+
+
+def reduce_candidate_shards(values, indices, index_offset, async_op=False):
     """Candidate-sharded stages (fewer sets than ranks): every rank holds the per-set maximum over
     ITS candidates, (values [S], local indices [S]).  Returns the maximum over all candidates with
     numpy's first-index tie rule (np.where(v == max)[0][0] over the concatenated candidate array,
-    acquisitionFunc.py:135-138): among equal values the lowest GLOBAL index wins.  One collective."""
+    acquisitionFunc.py:135-138): among equal values the lowest GLOBAL index wins.  One collective; on CUDA
+    tensors over NCCL the records are packed and reduced by one small kernel each (bf_records_pack /
+    bf_records_reduce).  async_op=True returns a handle whose result() gives the pair, so the caller can launch
+    more work behind the collective."""
     r, w = world()
-    gidx = indices + int(index_offset)
     if w == 1:
-        return values, gidx
+        out = (values, indices + int(index_offset))
+        return _Ready(out) if async_op else out
     dev = values.device
+    if values.is_cuda and dist.get_backend() == "nccl":
+        from . import _lib
+        S = values.numel()
+        pack = torch.empty((2 * S,), dtype=torch.float64, device=dev)
+        _lib.call("bf_records_pack", S, values.contiguous().data_ptr(), indices.to(torch.int64).contiguous().data_ptr(),
+                  int(index_offset), pack.data_ptr(), _lib.stream())
+        gathered = torch.empty((w * 2 * S,), dtype=torch.float64, device=dev)
+        work = dist.all_gather_into_tensor(gathered, pack, async_op=True)
+        handle = _ShardReduction(work, gathered, w, S, dev)
+        return handle if async_op else handle.result()
+    gidx = indices + int(index_offset)
     gv, gi = _gather_packed(values.contiguous(), gidx.to(torch.int64).contiguous())      # [world, S] each
     best = gv.max(dim=0).values
     cand = torch.where(gv == best, gi, torch.full_like(gi, _BIG))
-    return best.to(dev), cand.min(dim=0).values.to(dev)
+    out = (best.to(dev), cand.min(dim=0).values.to(dev))
+    return _Ready(out) if async_op else out
 
 
 def reduce_top2(t1, i1, t2, index_offset):

@@ -504,9 +504,10 @@ def run_gpu(args):
         f = engine.build_factors(KERNEL, Xt, yt, hp[:, 1:], hp[:, 0], sn, ndim=N_DIM, check=False)
         res = engine.posterior_sweep(f, Xs_dev, acq_mask=mask, spread_is_sqrt=False, curr_max=curr_max,
                                      xi=XI, kt=kt)
-        # candidate-sharded: per-rank maxima -> all-gather -> first global index among equal values
+        # candidate-sharded: per-rank maxima -> all-gather -> first global index among equal values.  The
+        # collective is left in flight (async handle): the next step's set-up and sweep are launched behind it
         return bdist.reduce_candidate_shards(res.best_val[0, :3].contiguous(), res.best_idx[0, :3].contiguous(),
-                                             rank * N_CAND)
+                                             rank * N_CAND, async_op=True)
 
     # end to end through the reference-facing call: the truth GP object of the batch-only path
     # (barefoot.py:771-773) and one util call per work item with HOST candidates (pinned memory)
@@ -517,8 +518,13 @@ def run_gpu(args):
                                            XI, return_device=True)
         vals = torch.stack([out[nm][0][0] for nm in ("EI", "PI", "UCB")])
         idxs = torch.stack([out[nm][1][0] for nm in ("EI", "PI", "UCB")])
-        v, i = bdist.reduce_candidate_shards(vals, idxs, rank * N_CAND)
-        return v.cpu(), i.cpu()
+        h = bdist.reduce_candidate_shards(vals, idxs, rank * N_CAND, async_op=True)
+
+        class _Read:                                   # the step's device -> host read of its result
+            def result(self_inner):
+                v, i = h.result()
+                return v.cpu(), i.cpu()
+        return _Read()
 
     def barrier():
         if world > 1:
@@ -526,8 +532,11 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup):
+        """K steps, software-pipelined two deep: step s + 1 is launched (its host -> device copy runs on the copy
+        stream, its kernels queue behind step s) before the result of step s is read, so copies, collectives and
+        result reads overlap the neighbouring step's sweep.  Every step's copy and read are inside the timed region."""
         for w in range(warmup):
-            fn(w % RING)
+            fn(w % RING).result()
         barrier()
         clocks = ClockSampler(local_rank)
         clocks.start()
@@ -536,8 +545,13 @@ def run_gpu(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
+        pending = None
         for s in range(steps):
-            out = fn((warmup + s) % RING)
+            nxt = fn((warmup + s) % RING)
+            if pending is not None:
+                out = pending.result()
+            pending = nxt
+        out = pending.result()
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -555,7 +569,8 @@ def run_gpu(args):
     steps, warmup = args.steps, max(3, args.warmup)
     ms, kern_ms, launches, clocks, _, out = timed(lambda b: step(dev_batches[b], Xd, yd), steps, warmup)
     ms_e2e, _, _, _, wall_e2e, out_e2e = timed(step_e2e, steps, warmup)
-    # an e2e step ends with a blocking device->host read, so the host clock is the honest one
+    # an e2e step ends with a blocking device->host read, so the host clock is the honest one (the reads of the
+    # pipelined steps all happen before the clock stops)
     ms_e2e = max(ms_e2e, wall_e2e * 1e3)
     if world > 1:
         t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)

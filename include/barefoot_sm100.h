@@ -185,6 +185,13 @@ int bf_acq_eval(int kind, long long N, int S, const double* y, const double* spr
                 double curr_max, double xi, double kt, double* out, double* part_val,
                 long long* part_idx, double* best_val, long long* best_idx, void* stream);
 
+/* Candidate-sharded stages over several GPUs: every rank holds the per-set maximum over ITS
+ * candidates.  bf_records_pack writes val [S] and (idx + offset) [S] into one [2 x S] buffer for a single
+ * all-gather; bf_records_reduce turns the gathered [world x 2 x S] buffer into the per-set maximum with numpy's
+ * first-index tie rule over the concatenated candidates (lowest global index among equal values). */
+int bf_records_pack(int S, const double* val, const long long* idx, long long offset, double* out, void* stream);
+int bf_records_reduce(int world, int S, const double* gathered, double* best_val, long long* best_idx, void* stream);
+
 /* ---- (4) knowledge gradient on a DENSE covariance (Frazier's sort / unique / upper-envelope
  * algorithm): acquisitionFunc.py:12-96 as the batch-only path calls it, util.py:1078-1081 ------- */
 /* mu [S x N], sigma [S x N x N] (column i of sigma is read for candidate i, as the reference does),
