@@ -47,10 +47,63 @@ def to_dev_async(a, dtype=F64):
     return out, ev
 
 
+_read_stream = None
+
+
+class AsyncRead:
+    """Device -> host read of small result tensors that does NOT queue behind later work on the compute stream:
+    the copies run on a read-back stream after an event recorded now, into pinned buffers; result() waits for
+    them only.  `prepare` (optional) is called on the read-back stream first and returns the tensors to read
+    (e.g. the wait + final kernel of an asynchronous cross-rank reduction).  A caller that pipelines work items
+    (launch item s + 1, then read item s) keeps the GPU busy: with a plain .cpu() the read of item s would sit
+    behind the sweep of item s + 1 in stream order and the queue would drain every step."""
+
+    def __init__(self, tensors=(), prepare=None):
+        global _read_stream
+        dev = device()
+        if _read_stream is None:
+            _read_stream = torch.cuda.Stream(device=dev)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._keep = list(tensors)
+        with torch.cuda.stream(_read_stream):
+            _read_stream.wait_event(ev)
+            src = list(prepare()) if prepare is not None else []
+            src += list(tensors)
+            self._keep += src
+            self.host = []
+            for t in src:
+                h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                h.copy_(t, non_blocking=True)
+                self.host.append(h)
+            self.done = torch.cuda.Event()
+            self.done.record(_read_stream)
+
+    def result(self):
+        self.done.synchronize()
+        self._keep = None
+        return self.host
+
+
+_PIN_BELOW = 1 << 20        # bytes
+
+
 def to_dev(a, dtype=F64):
+    """Host array / tensor -> device tensor on the current stream.  Small host arrays (the per-call
+    hyper-parameter rows, training data, scalars) go through pinned staging with an asynchronous copy: a copy
+    from pageable memory makes the host wait until the stream has drained, which would serialise a caller that
+    pipelines work items (the next item's set-up could not even be queued before the previous sweep ends)."""
     if isinstance(a, torch.Tensor):
-        return a.to(device=device(), dtype=dtype).contiguous()
-    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device())
+        if a.is_cuda or a.numel() * a.element_size() >= _PIN_BELOW or a.is_pinned():
+            return a.to(device=device(), dtype=dtype, non_blocking=a.is_pinned() if not a.is_cuda else False).contiguous()
+        t = a.to(dtype=dtype).contiguous()
+    else:
+        t = torch.as_tensor(np.ascontiguousarray(a), dtype=dtype)
+        if t.numel() * t.element_size() >= _PIN_BELOW:
+            return t.to(device())
+    if t.numel() == 0:
+        return t.to(device())
+    return t.pin_memory().to(device(), non_blocking=True)
 
 
 def amplitude(sigma_f, ndim):

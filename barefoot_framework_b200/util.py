@@ -410,7 +410,8 @@ def batch_acquisition_multi(modelGP, hp_sets, x_test, curr_max, names=("EI", "PI
     """Several elementwise acquisitions of the batch-only work item (util.py:913-1129) from ONE posterior
     sweep: GP set-up for every hyper-parameter set, posterior over x_test (host array, pinned host tensor or
     device tensor), then every requested acquisition fused into the epilogue.  Returns
-    {name: (values [H], indices [H])} as host arrays, or device tensors with return_device."""
+    {name: (values [H], indices [H])} as host arrays, or device tensors with return_device (plus "status" for
+    check_status, see below)."""
     hp = np.atleast_2d(np.asarray(hp_sets, dtype=np.float64))
     # the candidates travel host -> device on a side stream while the GPs are factorised
     x_test, copied = engine.to_dev_async(x_test)
@@ -432,11 +433,24 @@ def batch_acquisition_multi(modelGP, hp_sets, x_test, curr_max, names=("EI", "PI
     res = engine.posterior_sweep(f, x_test, None if shift is None else torch.ones_like(shift), shift, acq_mask=mask,
                                  spread_is_sqrt=False, curr_max=curr_max, xi=xi,
                                  kt=engine.ucb_kt(f.d, iteration) if "UCB" in names else 0.0)
-    f.raise_if_not_positive_definite()
     if return_device:
-        return {nm: (res.best_val[:, _SLOTS[nm]], res.best_idx[:, _SLOTS[nm]]) for nm in names}
+        # nothing is read back here: the caller reads the records when it needs them and hands "status" (the
+        # per-set factorisation status, 0 = ok) to check_status() at that point, so consecutive work items
+        # pipeline (the next item's copy and set-up are queued while this sweep runs)
+        out = {nm: (res.best_val[:, _SLOTS[nm]], res.best_idx[:, _SLOTS[nm]]) for nm in names}
+        out["status"] = f.info
+        return out
+    f.raise_if_not_positive_definite()
     bv, bi = res.best_val.cpu().numpy(), res.best_idx.cpu().numpy()
     return {nm: (bv[:, _SLOTS[nm]].copy(), bi[:, _SLOTS[nm]].copy()) for nm in names}
+
+
+def check_status(status):
+    """Raise what george / SciPy raise from the Cholesky factorisation (gpModel.py:41) if any set of a
+    return_device call was not positive definite; `status` is that call's "status" entry (device or host)."""
+    bad = int(torch.as_tensor(status).max().item()) if len(status) else 0
+    if bad:
+        raise np.linalg.LinAlgError("%d-th leading minor of a GP kernel matrix is not positive definite" % bad)
 
 
 def batchAcquisitionFunc(param):

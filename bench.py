@@ -519,11 +519,15 @@ def run_gpu(args):
         vals = torch.stack([out[nm][0][0] for nm in ("EI", "PI", "UCB")])
         idxs = torch.stack([out[nm][1][0] for nm in ("EI", "PI", "UCB")])
         h = bdist.reduce_candidate_shards(vals, idxs, rank * N_CAND, async_op=True)
+        # the step's device -> host read (records + factorisation status) on the read-back stream, so that it
+        # does not queue behind the next step's sweep
+        rd = engine.AsyncRead([out["status"]], prepare=h.result)
 
-        class _Read:                                   # the step's device -> host read of its result
+        class _Read:
             def result(self_inner):
-                v, i = h.result()
-                return v.cpu(), i.cpu()
+                v, i, status = rd.result()
+                util.check_status(status)
+                return v, i
         return _Read()
 
     def barrier():
@@ -576,7 +580,7 @@ def run_gpu(args):
         t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
-    d2h_bytes = 3 * 8 + 3 * 8
+    d2h_bytes = 3 * 8 + 3 * 8 + 4                  # three (value, index) records + the factorisation status
 
     evals = float(N_CAND) * world * steps
     value = evals / (ms * 1e-3)
