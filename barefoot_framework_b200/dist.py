@@ -61,8 +61,12 @@ def gather_host_sets(values, indices, n_total=None):
     if w == 1:
         return values, indices
     import numpy as np
-    v, i = gather_sets(torch.as_tensor(np.ascontiguousarray(values, dtype=np.float64)),
-                       torch.as_tensor(np.ascontiguousarray(indices, dtype=np.int64)), n_total)
+    tv = torch.as_tensor(np.ascontiguousarray(values, dtype=np.float64))
+    ti = torch.as_tensor(np.ascontiguousarray(indices, dtype=np.int64))
+    if dist.get_backend() == "nccl":            # NCCL exchanges device tensors only
+        dev = torch.device("cuda", torch.cuda.current_device())
+        tv, ti = tv.to(dev), ti.to(dev)
+    v, i = gather_sets(tv, ti, n_total)
     return v.cpu().numpy(), i.cpu().numpy()
 
 
@@ -79,8 +83,11 @@ def shard_range(n, rank=None, world_size=None):
 
 def _comm(t):
     """gloo (CPU tests, or ranks sharing one GPU) exchanges host tensors; NCCL device tensors."""
-    if dist.get_backend() == "gloo" and t.is_cuda:
+    backend = dist.get_backend()
+    if backend == "gloo" and t.is_cuda:
         return t.cpu()
+    if backend == "nccl" and not t.is_cuda:
+        return t.to(torch.device("cuda", torch.cuda.current_device()))
     return t
 
 
