@@ -89,6 +89,24 @@ def main():
     f1 = engine.build_factors("M52", X, y, rng.uniform(0.1, 1.0, size=(1, d)) ** 2, [1.0], 0.05, keep_dense=True)
     xs = rng.random((Nc, d))
     timed("predict_cov_plus_kg_full_2048", lambda: engine.kg_full_from_factors(f1, xs), Nc, "candidates")
+    # the scratch-memory variant beyond 4096 candidates: 8192 lines per candidate, 512 candidates scored, 2 sets
+    Nb, Mb = 8192, 512
+    Bm = rng.normal(size=(Nb, 16))
+    sig = engine.to_dev(np.stack([Bm @ Bm.T / 16 + 1e-3 * np.eye(Nb)] * 2))
+    mub = engine.to_dev(rng.normal(size=(2, Nb)))
+    timed("kg_full_scratch_N8192_M512_S2", lambda: engine.kg_full(mub, sig, M=Mb), 2 * Mb, "candidates")
+    del sig
+    # ROM-stage fantasy targets: 50 fantasy points of one ROM through the bordered append, batched reification
+    from barefoot_framework_b200.reificationFusion import model_reification
+    xt3 = [rng.random((200, d)) for _ in range(3)]
+    yt3 = [np.sin(6 * x).sum(axis=1) for x in xt3]
+    xtr = rng.random((50, d))
+    mr = model_reification(xt3, yt3, rng.uniform(0.1, 0.5, size=(3, d)), [1.0] * 3, [0.05] * 3, [0.0] * 3, [1.0] * 3,
+                           rng.uniform(0.1, 0.5, size=(3, d)), [1.0] * 3, [0.01] * 3, xtr, np.sin(6 * xtr).sum(axis=1), 3, d, "M52")
+    xf = rng.random((500, d))
+    bm, bv = mr.fused_rows_device(xf)
+    xn = rng.random((50, d))
+    timed("rom_fantasy_targets_K50_F500", lambda: mr.fantasy_targets_batched(xf, xn, np.zeros(50), 1, bm, bv), 50, "groups")
     print(json.dumps(out))
 
 
