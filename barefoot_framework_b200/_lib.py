@@ -72,6 +72,8 @@ SIGNATURES = {
     "bf_fantasy_rows": (c_i, [c_i, c_i, c_p, c_p, c_p, c_ll, c_p, c_p, c_p, c_d, c_d, c_d, c_d, c_p, c_p, c_p, c_p]),
     "bf_probe_dmma_flop": (c_d, [c_i, c_i]),
     "bf_probe_dmma": (c_i, [c_i, c_i, c_p, c_p]),
+    "bf_kmedoids_matrix_assign": (c_i, [c_ll, c_i, c_p, c_ll, c_p, c_p, c_p]),
+    "bf_kmedoids_matrix_update": (c_i, [c_ll, c_i, c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_p]),
     "bf_group_best": (c_i, [c_ll, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "bf_affine": (c_i, [c_ll, c_p, c_d, c_d, c_p, c_p]),
     "bf_total_variance": (c_i, [c_ll, c_p, c_d, c_d, c_p, c_d, c_p, c_p]),
@@ -122,7 +124,7 @@ def stream():
 
 
 # kernels per exported call, for the launch counter
-_KERNELS_PER_CALL = {"bf_kg_diag": 2, "bf_acq_eval": 2, "bf_gp_solve_rows": 3, "bf_kg_full": 2}
+_KERNELS_PER_CALL = {"bf_kmedoids_matrix_update": 2, "bf_kg_diag": 2, "bf_acq_eval": 2, "bf_gp_solve_rows": 3, "bf_kg_full": 2}
 
 
 def call(name, *args):

@@ -93,17 +93,18 @@ def to_dev(a, dtype=F64):
     hyper-parameter rows, training data, scalars) go through pinned staging with an asynchronous copy: a copy
     from pageable memory makes the host wait until the stream has drained, which would serialise a caller that
     pipelines work items (the next item's set-up could not even be queued before the previous sweep ends)."""
+    dev = device()                               # raises without a CUDA device: there is no CPU path
     if isinstance(a, torch.Tensor):
         if a.is_cuda or a.numel() * a.element_size() >= _PIN_BELOW or a.is_pinned():
-            return a.to(device=device(), dtype=dtype, non_blocking=a.is_pinned() if not a.is_cuda else False).contiguous()
+            return a.to(device=dev, dtype=dtype, non_blocking=a.is_pinned() if not a.is_cuda else False).contiguous()
         t = a.to(dtype=dtype).contiguous()
     else:
         t = torch.as_tensor(np.ascontiguousarray(a), dtype=dtype)
         if t.numel() * t.element_size() >= _PIN_BELOW:
-            return t.to(device())
+            return t.to(dev)
     if t.numel() == 0:
-        return t.to(device())
-    return t.pin_memory().to(device(), non_blocking=True)
+        return t.to(dev)
+    return t.pin_memory().to(dev, non_blocking=True)
 
 
 def amplitude(sigma_f, ndim):

@@ -257,6 +257,15 @@ int bf_kmedoids_iteration(long long N, int f, int k, const double* X, long long*
                           int32_t* labels, long long* perm, long long* seg, void* workspace, int part,
                           int nparts, double* cost, double* records, int32_t* changed, void* stream);
 
+/* ---- k-medoids on an explicit distance matrix: the vendored kMedoids(D, k, tmax), kmedoids.py:168-227 -------- */
+/* D [n x ld] row-major.  assign: labels[i] = first argmin_c D[i, M[c]] (:208).  update: after
+ * bf_kmedoids_sort_labels, cost[p] = mean of D[perm[p], perm[q]] over p's cluster (:213) and Mnew[c] = the
+ * cluster's first minimum (:214-215, always moves); empty[0] counts empty clusters (zero it first). */
+int bf_kmedoids_matrix_assign(long long n, int k, const double* D, long long ld, const long long* M,
+                              int32_t* labels, void* stream);
+int bf_kmedoids_matrix_update(long long n, int k, const double* D, long long ld, const long long* perm,
+                              const long long* seg, double* cost, long long* Mnew, int32_t* empty, void* stream);
+
 /* ---- clustering glue: barefoot.__kg_calc_clustering, barefoot.py:2102-2140 ---------------------- */
 /* Records r < R carry key[r] in [0, G) (selected candidate x* and model folded into one key) and
  * value[r].  Per group, the reference's in-order scan: the first record sets (value, row), a later one

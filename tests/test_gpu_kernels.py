@@ -687,3 +687,30 @@ def test_kg_full_scratch_and_shared_memory_kernels_agree_bit_for_bit(eng):
     _, _, nu_big = eng.kg_full(mu2, sigma2, M=M)
     a, b = nu_small.cpu().numpy()[0], nu_big.cpu().numpy()[0]
     np.testing.assert_allclose(b, a, rtol=1e-13, atol=0)
+
+
+def test_vendored_kmedoids_on_a_distance_matrix_matches_the_reference(eng):
+    """kmedoids.kMedoids(D, k, tmax) (the reference's vendored function, kmedoids.py:168-227) on the device
+    against goldens from the UNMODIFIED function (oracle/gen_kmedoids_vendored.py): same global-RNG consumption in
+    the initialisation (incl. duplicated points), same medoids and cluster memberships, early stop at tmax."""
+    from scipy.spatial import distance_matrix
+    from barefoot_framework_b200 import kmedoids
+    g = golden("kmedoids_vendored.npz")
+    for c in range(int(g["ncases"])):
+        P = g["c%d_P" % c]
+        D = distance_matrix(P, P)
+        np.random.seed(int(g["c%d_seed" % c]))
+        M, C = kmedoids.kMedoids(D, int(g["c%d_k" % c]), int(g["c%d_tmax" % c]))
+        np.testing.assert_array_equal(M, g["c%d_M" % c], err_msg=str(c))
+        lab = np.full(P.shape[0], -1, dtype=np.int64)
+        for kappa, idx in C.items():
+            lab[idx] = kappa
+        np.testing.assert_array_equal(lab, g["c%d_labels" % c], err_msg=str(c))
+    # and the round-1 golden of the same function
+    g1 = golden("kmedoids.npz")
+    P = g1["P"]
+    np.random.seed(7)
+    M, C = kmedoids.kMedoids(distance_matrix(P, P), 4)
+    np.testing.assert_array_equal(M, g1["kM_M"])
+    with pytest.raises(Exception):
+        kmedoids.kMedoids(distance_matrix(P, P), P.shape[0] + 1)
