@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(BF_LL_THREADS, BF_LL_CTAS_PER_SM) bf_cholesky_
 
     if (threadIdx.x == 0) bad = 0;
     if (GEN && threadIdx.x < p.d) w_s[threadIdx.x] = bf_metric_scale(p.kern, p.inv_l2[(size_t)hp * p.d + threadIdx.x]);
-    if (threadIdx.x < BF_EXP_TAB_N) tab[threadIdx.x] = bf_exp_tab_g[threadIdx.x];
+    for (int e = threadIdx.x; e < BF_EXP_TAB_N; e += BF_LL_THREADS) tab[e] = bf_exp_tab_g[e];
     __syncthreads();
     if (GEN) {
         for (int e = threadIdx.x; e < np * p.d; e += BF_LL_THREADS) {

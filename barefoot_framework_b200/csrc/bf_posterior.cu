@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(BF_THREADS, MINB) bf_posterior_kernel(PostPara
 
     for (int e = threadIdx.x; e < BF_WARPS * NT; e += BF_THREADS) spart[e] = 0.0;
     if (threadIdx.x < dd) w_s[threadIdx.x] = bf_metric_scale(p.kern, p.inv_l2[(size_t)hp * dd + threadIdx.x]);
-    if (threadIdx.x < BF_EXP_TAB_N) tab_s[threadIdx.x] = bf_exp_tab_g[threadIdx.x];
+    for (int e = threadIdx.x; e < BF_EXP_TAB_N; e += BF_THREADS) tab_s[e] = bf_exp_tab_g[e];
     __syncthreads();
     for (int e = threadIdx.x; e < dd * NT; e += BF_THREADS) {        // candidates, pre-scaled by the metric
         const int a = e / NT, c = e - a * NT;
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(BF_DUAL_THREADS, 1) bf_posterior_dual_kernel(P
 
     for (int e = gtid; e < BF_WARPS * NT; e += BF_THREADS) spart[e] = 0.0;   // idle-queue slots stay 0
     if (threadIdx.x < dd) w_s[threadIdx.x] = bf_metric_scale(p.kern, p.inv_l2[(size_t)hp * dd + threadIdx.x]);
-    if (threadIdx.x < BF_EXP_TAB_N) tab_s[threadIdx.x] = bf_exp_tab_g[threadIdx.x];
+    for (int e = threadIdx.x; e < BF_EXP_TAB_N; e += BF_DUAL_THREADS) tab_s[e] = bf_exp_tab_g[e];
     __syncthreads();
 
     BfBest best[3];

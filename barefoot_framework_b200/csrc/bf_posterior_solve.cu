@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(SV_THREADS, 1) bf_posterior_solve_kernel(Solve
 
     // ---- right-hand sides: k*(X, candidates) and y ----
     if (threadIdx.x < dd) w_s[threadIdx.x] = bf_metric_scale(p.kern, p.inv_l2[(size_t)hp * dd + threadIdx.x]);
-    if (threadIdx.x < BF_EXP_TAB_N) tab_s[threadIdx.x] = bf_exp_tab_g[threadIdx.x];
+    for (int e = threadIdx.x; e < BF_EXP_TAB_N; e += SV_THREADS) tab_s[e] = bf_exp_tab_g[e];
     __syncthreads();
     for (int e = threadIdx.x; e < dd * NCOL; e += SV_THREADS) {
         const int a = e / NCOL, col = e - a * NCOL;

@@ -714,3 +714,31 @@ def test_vendored_kmedoids_on_a_distance_matrix_matches_the_reference(eng):
     np.testing.assert_array_equal(M, g1["kM_M"])
     with pytest.raises(Exception):
         kmedoids.kMedoids(distance_matrix(P, P), P.shape[0] + 1)
+
+
+def test_device_exp_accuracy_over_the_whole_range(eng):
+    """bf_exp_nonpos (256-entry table, degree-4 polynomial, integer range / NaN tests) through the SE kernel
+    matrix in one dimension: K[i, j] = exp(-q) with q = (x_i - x_j)^2 / (2 l^2) spanning [0, 760].  The argument
+    itself carries a rounding of ~3e-16 q (pre-scaled coordinates), so the bound is (4e-16 q + 3e-16) relative;
+    below 2^-1022 the result is 0; a NaN length scale must reach the Cholesky status (no silent zero)."""
+    import torch
+    from barefoot_framework_b200._lib import KERN, call, ptr, stream
+    n = 512
+    x = np.linspace(0.0, 1.0, n)[:, None]
+    l = 1.0 / np.sqrt(2 * 760.0)                       # q = 760 (x_i - x_j)^2
+    lib = eng._lib.load()
+    np_ = lib.bf_padded_n(n)
+    K = torch.empty((1, np_, np_), dtype=torch.float64, device=eng.device())
+    call("bf_kernel_matrix", KERN["SE"], n, 1, 1, ptr(eng.to_dev(x)), ptr(eng.to_dev(eng.inv_metric(np.array([[l * l]])))),
+         ptr(eng.to_dev(np.array([1.0]))), None, ptr(eng.to_dev(np.array([0.0]))), 1, 0, ptr(K), stream())
+    got = K.cpu().numpy()[0, :n, :n]
+    q = 0.5 * (x - x.T) ** 2 * np.exp(-np.log(l * l))
+    ref = np.exp(-q)
+    off = ~np.eye(n, dtype=bool)
+    big = off & (ref > 2.3e-308)
+    rel = np.abs(got[big] - ref[big]) / ref[big]
+    assert (rel <= 4e-16 * q[big] + 3e-16).all(), rel.max()
+    assert (got[off & (q > 709.0)] == 0.0).all()
+    assert np.isfinite(got).all()
+    with pytest.raises(np.linalg.LinAlgError):
+        eng.build_factors("SE", x, np.zeros(n), np.array([[np.nan]]), [1.0], 0.05)
