@@ -155,8 +155,12 @@ class _ShardReduction:
     after the producing kernels): result() makes the current stream wait for it and applies the first-index
     maximum with one small kernel.  Lets the next step's set-up and sweep start behind the collective."""
 
-    def __init__(self, work, gathered, world_size, S, device):
-        self.work, self.gathered, self.world_size, self.S, self.device = work, gathered, world_size, S, device
+    def __init__(self, work, pack, gathered, world_size, S, device):
+        # `pack` is read by the collective on NCCL's stream: it must stay allocated until the collective has run
+        # (a freed block is handed to the NEXT work item's tensors on the compute stream, whose kernels are not
+        # ordered against NCCL's read - found by tools/dbg/pipeline_stress.py: records of neighbouring items mixed)
+        self.work, self.pack, self.gathered = work, pack, gathered
+        self.world_size, self.S, self.device = world_size, S, device
 
     def result(self):
         from . import _lib
@@ -166,6 +170,10 @@ class _ShardReduction:
         best_idx = torch.empty((self.S,), dtype=torch.int64, device=self.device)
         _lib.call("bf_records_reduce", self.world_size, self.S, self.gathered.data_ptr(), best_val.data_ptr(),
                   best_idx.data_ptr(), _lib.stream())
+        # the caller's stream now orders everything after the collective; the buffers may be released once the
+        # reduce kernel has run - record that stream so the allocator waits for it
+        self.gathered.record_stream(torch.cuda.current_stream())
+        self.pack = None
         return best_val, best_idx
 
 
@@ -198,7 +206,7 @@ def reduce_candidate_shards(values, indices, index_offset, async_op=False):
                   int(index_offset), pack.data_ptr(), _lib.stream())
         gathered = torch.empty((w * 2 * S,), dtype=torch.float64, device=dev)
         work = dist.all_gather_into_tensor(gathered, pack, async_op=True)
-        handle = _ShardReduction(work, gathered, w, S, dev)
+        handle = _ShardReduction(work, pack, gathered, w, S, dev)
         return handle if async_op else handle.result()
     gidx = indices + int(index_offset)
     gv, gi = _gather_packed(values.contiguous(), gidx.to(torch.int64).contiguous())      # [world, S] each

@@ -98,6 +98,34 @@ def _sweep(f, scale, shift, x_test, names, stage, curr_max, iteration, xi, M=Non
     return out
 
 
+def _sweep_candidate_sharded(f, scale, shift, x_test, name, stage, curr_max, iteration, xi, M=None):
+    """_sweep for ONE deterministic acquisition when there are fewer sets than ranks (reification-only runs have
+    H = 1): the CANDIDATES are split over the ranks instead (SURVEY.md 8e "secondary: candidate tiles"), every rank
+    sweeps its tile for all sets, and the per-rank records are combined with numpy's first-index rule
+    (dist.reduce_candidate_shards).  KG needs the top two fused means over ALL candidates first
+    (dist.reduce_top2), then the closed form runs locally.  Returns (values [S], global indices [S]) on the host."""
+    N = x_test.shape[0]
+    lo, hi = bdist.shard_range(N)
+    kg = name == "KG"
+    mask = ACQ_GREEDY | ACQ_BITS.get(name, 0)
+    kt = engine.ucb_kt(f.d, iteration) if name == "UCB" else 0.0
+    res = engine.posterior_sweep(f, x_test[lo:hi], scale, shift, want_mu=kg, want_var=kg, acq_mask=mask,
+                                 spread_is_sqrt=(stage == "ROM"), curr_max=curr_max, xi=xi, kt=kt)
+    if not kg:
+        slot = _SLOTS[name]
+        v, i = bdist.reduce_candidate_shards(res.best_val[:, slot].contiguous(), res.best_idx[:, slot].contiguous(), lo)
+        return v.cpu().numpy(), i.cpu().numpy()
+    t1, gi1, t2 = bdist.reduce_top2(res.best_val[:, SLOT_GREEDY].contiguous(), res.best_idx[:, SLOT_GREEDY].contiguous(),
+                                    res.best_val[:, engine.SLOT_TOP2].contiguous(), lo)
+    res.best_val[:, SLOT_GREEDY], res.best_val[:, engine.SLOT_TOP2] = t1, t2
+    res.best_idx[:, SLOT_GREEDY] = gi1 - lo                     # local position of the global arg-max (or outside the tile)
+    m_total = N if M is None else int(M)
+    v, i, _ = engine.kg_from_sweep(res, M=max(0, min(hi, m_total) - lo), sn=SN_KG)
+    v, i = bdist.reduce_candidate_shards(v, i, lo)
+    i = torch.where(v > 0, i, torch.zeros_like(i))              # nothing above the reference's floor: (0, index 0)
+    return v.cpu().numpy(), i.cpu().numpy()
+
+
 _HEDGE_ORDER = ("KG", "TS", "EI", "Greedy", "PI", "UCB")      # util.py:626-654, 733-789
 
 
@@ -111,8 +139,18 @@ def fused_calculate_batch(model, x_fused, hp_sets, kernel, x_test, curr_max, sam
     x_test = np.asarray(x_test, dtype=np.float64)
     hp = np.atleast_2d(np.asarray(hp_sets, dtype=np.float64))
     deterministic = sampleOpt not in ("Hedge", "TS")          # host RNG draws must stay in one stream
-    lo, hi = bdist.shard_range(hp.shape[0]) if deterministic else (0, hp.shape[0])
     name = sampleOpt if sampleOpt in ("KG", "TS", "EI", "PI", "UCB") else "Greedy"
+    world = bdist.world()[1]
+    if deterministic and world > 1 and hp.shape[0] < world <= x_test.shape[0]:
+        # fewer sets than ranks (H = 1 in reification-only runs): split the candidates instead
+        err = out = None
+        try:
+            f, scale, shift = model.create_fused_GP_batch(x_fused, hp, kernel, targets=targets)
+        except Exception as e:                                 # noqa: BLE001 - identical on every rank (same sets)
+            err = e
+        bdist.raise_together(err, "fused_calculate_batch")
+        return _sweep_candidate_sharded(f, scale, shift, x_test, name, "TM", curr_max, iteration, xi)
+    lo, hi = bdist.shard_range(hp.shape[0]) if deterministic else (0, hp.shape[0])
     err = r = f = None
     try:
         f, scale, shift = model.create_fused_GP_batch(x_fused, hp[lo:hi], kernel, targets=targets)
@@ -369,12 +407,26 @@ def batch_acquisition_batch(modelGP, hp_sets, x_test, curr_max, acqFunc, iterati
     x_test = np.asarray(x_test, dtype=np.float64)
     hp = np.atleast_2d(np.asarray(hp_sets, dtype=np.float64))
     H_total = hp.shape[0]
-    if acqFunc not in ("KG", "Hedge", "TS"):
+    world = bdist.world()[1]
+    by_candidates = acqFunc not in ("KG", "Hedge", "TS") and world > 1 and H_total < world <= x_test.shape[0]
+    if acqFunc not in ("KG", "Hedge", "TS") and not by_candidates:
         lo, hi = bdist.shard_range(H_total)               # sets sharded over ranks, gathered below
         hp = hp[lo:hi]
     x = np.asarray(modelGP.x_train, dtype=np.float64)
     x = x.reshape(x.shape[0], -1)
     y = np.asarray(modelGP.y_train, dtype=np.float64) - float(modelGP.mean)
+    if by_candidates:
+        # fewer sets than ranks: every rank factorises all sets and sweeps ITS candidate tile
+        err = None
+        try:
+            f = engine.build_factors(modelGP.kern, x, y, hp[:, 1:], hp[:, 0], modelGP.sigma_n, ndim=modelGP.n_dim)
+        except Exception as e:                                 # noqa: BLE001 - identical on every rank
+            err = e
+        bdist.raise_together(err, "batch_acquisition_batch")
+        shift = torch.full((f.S,), float(modelGP.mean), dtype=engine.F64, device=f.X.device) if modelGP.mean else None
+        nm = acqFunc if acqFunc in ("EI", "PI", "UCB") else "Greedy"
+        return _sweep_candidate_sharded(f, None if shift is None else torch.ones_like(shift), shift, x_test, nm, "BATCH",
+                                        curr_max, iteration, xi)
     sharded = acqFunc not in ("KG", "Hedge", "TS")
     name = acqFunc if acqFunc in ("TS", "EI", "PI", "UCB") else "Greedy"
     err = r = f = None

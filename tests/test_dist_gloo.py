@@ -302,3 +302,42 @@ def test_batch_only_stage_sharded_over_two_ranks_matches_oracle():
                 rv, ri = fast.acquisition(acq, mu, var, float(y.max()), d, 2, "BATCH")
                 assert ri == int(i[h]), (acq, h)
                 assert abs(rv - v[h]) <= 1e-9 * max(1.0, abs(rv)), (acq, h)
+
+
+def _tm_stage_candidate_sharded(rank, world):
+    """H = 1 (< 2 ranks): the candidates are split over the ranks instead of the sets - KG (global top-2 first),
+    EI and Greedy of the fused GP, and EI / UCB of the batch-only path - against the unsharded goldens."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    from conftest import golden
+    from barefoot_framework_b200 import reificationFusion, util
+    from barefoot_framework_b200.gpModel import gp_model
+    g = golden("workitems.npz")
+    out = {}
+    for pre in ("c1_", "c3_"):
+        model = reificationFusion.model_reification(
+            [g[pre + f"x_train{i}"].copy() for i in range(3)], [g[pre + f"y_train{i}"].copy() for i in range(3)],
+            g[pre + "model_l"], g[pre + "model_sf"], g[pre + "model_sn"], g[pre + "means"], g[pre + "std"],
+            g[pre + "err_l"], g[pre + "err_sf"], g[pre + "err_sn"], g[pre + "x_true"].copy(), g[pre + "y_true"].copy(),
+            3, int(g[pre + "d"]), str(g[pre + "kern"]))
+        for opt in ("KG", "EI", "Greedy"):
+            for h in range(min(3, g[pre + "hps"].shape[0])):
+                v, i = util.fused_calculate_batch(model, g[pre + "x_fused"], g[pre + "hps"][h:h + 1], str(g[pre + "kern"]),
+                                                  g[pre + "x_test"], float(g[pre + "curr_max"]), opt, iteration=3)
+                out[(pre, opt, h)] = (float(v[0]), int(i[0]), float(g[pre + f"tm_{opt}_val"][h]), int(g[pre + f"tm_{opt}_idx"][h]))
+    b = golden("batch.npz")
+    d = int(b["d"])
+    gp = gp_model(b["x"], b["y"], np.ones(d), 1, 0.05, d, str(b["k0_kern"]))
+    for opt in ("EI", "UCB"):
+        v, i = util.batch_acquisition_batch(gp, b["hps"][:1], b["x_test"], float(b["curr_max"]), opt, iteration=2)
+        out[("batch", opt, 0)] = (float(v[0]), int(i[0]), float(b[f"k0_{opt}_val"][0]), int(b[f"k0_{opt}_idx"][0]))
+    return out
+
+
+@pytest.mark.gpu
+def test_candidate_sharding_when_there_are_fewer_sets_than_ranks():
+    res = _run(_tm_stage_candidate_sharded)
+    for out in res:
+        for key, (v, i, rv, ri) in out.items():
+            assert i == ri, key
+            assert abs(v - rv) <= 1e-8 * max(1.0, abs(rv)) + 1e-11, key
