@@ -539,8 +539,14 @@ def run_gpu(args):
         """K steps, software-pipelined two deep: step s + 1 is launched (its host -> device copy runs on the copy
         stream, its kernels queue behind step s) before the result of step s is read, so copies, collectives and
         result reads overlap the neighbouring step's sweep.  Every step's copy and read are inside the timed region."""
-        for w in range(warmup):
-            fn(w % RING).result()
+        pending = None
+        for w in range(warmup):                      # same two-deep pattern as the timed loop, so the caching
+            nxt = fn(w % RING)                       # allocator already holds the blocks of two items in flight
+            if pending is not None:
+                pending.result()
+            pending = nxt
+        if pending is not None:
+            pending.result()
         barrier()
         clocks = ClockSampler(local_rank)
         clocks.start()
@@ -564,6 +570,9 @@ def run_gpu(args):
         kern_ms = [a.elapsed_time(b) for a, b in events]
         launches = _lib.launches - l0
         ck = clocks.stop()
+        if os.environ.get("BENCH_DEBUG"):
+            print("rank %d: %.3f ms/step device, %.3f ms/step host wall, kernel %.3f ms" %
+                  (rank, ms / steps, wall * 1e3 / steps, float(np.mean(kern_ms)) if kern_ms else 0.0), file=sys.stderr, flush=True)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
