@@ -472,7 +472,10 @@ def batch_acquisition_multi(modelGP, hp_sets, x_test, curr_max, names=("EI", "PI
     y = np.asarray(modelGP.y_train, dtype=np.float64) - float(modelGP.mean)
     # the factorisation status is read after the sweep (where the results are read anyway), so the host
     # does not stall between the set-up and the sweep
-    f = engine.build_factors(modelGP.kern, x, y, hp[:, 1:], hp[:, 0], modelGP.sigma_n, ndim=modelGP.n_dim, check=False)
+    # ... on a side stream, so that a caller who pipelines work items gets this item's set-up under the previous
+    # item's sweep (engine.build_factors_overlapped)
+    f = engine.build_factors_overlapped(modelGP.kern, x, y, hp[:, 1:], hp[:, 0], modelGP.sigma_n, ndim=modelGP.n_dim,
+                                        check=False)
     if copied is not None:
         torch.cuda.current_stream().wait_event(copied)
         x_test.record_stream(torch.cuda.current_stream())

@@ -501,7 +501,7 @@ def run_gpu(args):
 
     def step(Xs_dev, Xt, yt):
         # batch-only work item: l_param is NOT squared on this path (util.py:948, quirk Q1)
-        f = engine.build_factors(KERNEL, Xt, yt, hp[:, 1:], hp[:, 0], sn, ndim=N_DIM, check=False)
+        f = engine.build_factors_overlapped(KERNEL, Xt, yt, hp[:, 1:], hp[:, 0], sn, ndim=N_DIM, check=False)
         res = engine.posterior_sweep(f, Xs_dev, acq_mask=mask, spread_is_sqrt=False, curr_max=curr_max,
                                      xi=XI, kt=kt)
         # candidate-sharded: per-rank maxima -> all-gather -> first global index among equal values.  The

@@ -730,8 +730,9 @@ def test_device_exp_accuracy_over_the_whole_range(eng):
     lib = eng._lib.load()
     np_ = lib.bf_padded_n(n)
     K = torch.empty((1, np_, np_), dtype=torch.float64, device=eng.device())
-    call("bf_kernel_matrix", KERN["SE"], n, 1, 1, ptr(eng.to_dev(x)), ptr(eng.to_dev(eng.inv_metric(np.array([[l * l]])))),
-         ptr(eng.to_dev(np.array([1.0]))), None, ptr(eng.to_dev(np.array([0.0]))), 1, 0, ptr(K), stream())
+    xd, wd = eng.to_dev(x), eng.to_dev(eng.inv_metric(np.array([[l * l]])))     # keep the operands alive until the launch ran
+    ad, ed = eng.to_dev(np.array([1.0])), eng.to_dev(np.array([0.0]))
+    call("bf_kernel_matrix", KERN["SE"], n, 1, 1, ptr(xd), ptr(wd), ptr(ad), None, ptr(ed), 1, 0, ptr(K), stream())
     got = K.cpu().numpy()[0, :n, :n]
     q = 0.5 * (x - x.T) ** 2 * np.exp(-np.log(l * l))
     ref = np.exp(-q)
