@@ -11,13 +11,19 @@
 // One CTA = 8 NA - 1 candidates (+ the y column) of one set, 8 warps: warp w owns rows 8 (w & 3) .. + 7 of
 // every row block and the 8-column groups (w >> 2), (w >> 2) + 2, ...  Row block I:
 //     s = sum_{K < I} L_IK v_K;  v_I = L_II^-1 (rhs_I - s)
-// The A tiles (L_IK, then L_II^-1) stream from L2 through a cp.async ring; the right-hand sides are
-// generated into shared memory in DMMA B-fragment order and overwritten in place by the solution.
+// The A operand streams from L2 through a cp.async ring in UNITS of up to two horizontally adjacent 32 x 32
+// tiles of a row block (L[I, K..K+1], contiguous in the row-major factor), then L_II^-1: one wait + barrier per
+// unit, i.e. 80 instead of 136 synchronisations per CTA at n = 500.  (Measured in round 2: the kernel time did
+// not move - 1.7 us per set at n = 500, 50 candidates - so the barriers were not what holds the DMMA pipe at
+// 30 %: a CTA's 126 us split into ~35 us of DMMA issue at 8 warps, ~23 us of right-hand-side generation at the
+// FP64 latency of 8 warps per SM, 16 serial diagonal steps and the L2 stream; 222 kB of shared memory - 131 kB
+// of it the solution block V - keep it at one CTA per SM.)  The right-hand sides are generated into shared memory in DMMA B-fragment order and overwritten in
+// place by the solution.
 #include "bf_common.cuh"
 
 #define SV_THREADS 256
-#define SV_RING 6
-#define SV_TLD 36
+#define SV_RING 4                       // ring slots, one unit each
+#define SV_TLD 68                       // unit leading dimension (doubles): 64 columns + pad, conflict-free fragment reads
 
 struct SolveParams {
     int kern, n, d, np, nb, S;
@@ -58,23 +64,26 @@ __global__ void __launch_bounds__(SV_THREADS, 1) bf_posterior_solve_kernel(Solve
     const double* dinv = p.dinv + (size_t)set * nb * 1024;
     const double* yv = p.y + (size_t)set * p.y_stride;
 
-    // ---- tile stream: (I, K) for K = 0..I; K == I is the inverse of the diagonal block ----
-    const int M = nb * (nb + 1) / 2;
+    // ---- unit stream: row block I = units (I, K, w) with w = min(2, I - K) for K = 0, 2, .. < I, then the
+    //      inverse of the diagonal block ----
+    int U = 0;
+    for (int i = 0; i < nb; ++i) U += ((i + 1) >> 1) + 1;
     int pI = 0, pK = 0;
     auto request = [&](int slot) {
-        const bool diag = pK == pI;
+        const bool diag = pK >= pI;
+        const int w = diag ? 1 : (pI - pK >= 2 ? 2 : 1);
         const double* src = diag ? dinv + (size_t)pI * 1024 : L + (size_t)(32 * pI) * np + 32 * pK;
         const int ld = diag ? 32 : np;
         double* dst = ring + (size_t)slot * 32 * SV_TLD;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int e = threadIdx.x + SV_THREADS * q, row = e >> 4, ch = e & 15;
+        const int cpr = 16 * w;                              // 16-byte chunks per row
+        for (int e = threadIdx.x; e < 32 * cpr; e += SV_THREADS) {
+            const int row = e / cpr, ch = e - row * cpr;
             bf_cp_async16(dst + row * SV_TLD + 2 * ch, src + (size_t)row * ld + 2 * ch);
         }
-        if (pK < pI) ++pK; else { ++pI; pK = 0; }
+        if (diag) { ++pI; pK = 0; } else { pK += w; }
     };
     for (int t = 0; t < SV_RING - 1; ++t) {          // in flight while the right-hand sides are generated
-        if (t < M) request(t);
+        if (t < U) request(t);
         bf_cp_async_commit();
     }
 
@@ -123,23 +132,26 @@ __global__ void __launch_bounds__(SV_THREADS, 1) bf_posterior_solve_kernel(Solve
 #pragma unroll
         for (int h = 0; h < 4; ++h) acc[i][h][0] = acc[i][h][1] = 0.0;
     int I = 0, K = 0;
-    for (int t = 0; t < M; ++t) {
+    for (int t = 0; t < U; ++t) {
         bf_cp_async_wait<SV_RING - 2>();
-        __syncthreads();                               // tile t, the right-hand sides and v_{I-1} visible
-        if (t + SV_RING - 1 < M) request((t + SV_RING - 1) % SV_RING);
+        __syncthreads();                               // unit t, the right-hand sides and v_{I-1} visible
+        if (t + SV_RING - 1 < U) request((t + SV_RING - 1) % SV_RING);
         bf_cp_async_commit();
         const double* A = ring + (size_t)(t % SV_RING) * 32 * SV_TLD + (8 * tt + r) * SV_TLD + kk;
         if (K < I) {
+            const int w = I - K >= 2 ? 2 : 1;
+            for (int kt = 0; kt < w; ++kt) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                const double a = A[4 * ks];
+                for (int ks = 0; ks < 8; ++ks) {
+                    const double a = A[32 * kt + 4 * ks];
 #pragma unroll
-                for (int i = 0; i < NAW; ++i) {
-                    const double b = V[(size_t)(K * NA + nh + 2 * i) * 256 + (4 * ks + kk) * 8 + r];
-                    bf_dmma(acc[i][ks & 3][0], acc[i][ks & 3][1], a, b);
+                    for (int i = 0; i < NAW; ++i) {
+                        const double b = V[(size_t)((K + kt) * NA + nh + 2 * i) * 256 + (4 * ks + kk) * 8 + r];
+                        bf_dmma(acc[i][ks & 3][0], acc[i][ks & 3][1], a, b);
+                    }
                 }
             }
-            ++K;
+            K += w;
         } else {
 #pragma unroll
             for (int i = 0; i < NAW; ++i) {
