@@ -341,3 +341,36 @@ def test_candidate_sharding_when_there_are_fewer_sets_than_ranks():
         for key, (v, i, rv, ri) in out.items():
             assert i == ri, key
             assert abs(v - rv) <= 1e-8 * max(1.0, abs(rv)) + 1e-11, key
+
+
+def _orchestrator_two_ranks(rank, world):
+    """The whole orchestrator under two ranks (gloo, both on cuda:0): rank 0 is authoritative (RNG state, model
+    calls, wall-clock costs, files); the ROM-stage groups and the TM-stage sets are sharded.  Both ranks must
+    walk the same iterations and end with the reference's evaluated points; only rank 0 writes files."""
+    import sys
+    import tempfile
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    import toy_models
+    from barefoot_framework_b200 import dist as bd
+    from barefoot_framework_b200.barefoot import barefoot
+    workdir = bd.broadcast_object(tempfile.mkdtemp() if rank == 0 else None)
+    out = {}
+    for name in ("config1_se_kg", "reifi_m52_ei"):
+        case = [c for c in toy_models.CASES if c[0] == name][0]
+        ev, it = toy_models.run_case(barefoot, case[0] + "_2r", case[1], case[2], case[3], workdir)
+        out[name] = ev
+    out["files"] = sorted(os.listdir(os.path.join(workdir, "results"))) if rank == 0 else None
+    return out
+
+
+@pytest.mark.gpu
+def test_orchestrator_under_two_ranks_matches_the_reference():
+    from conftest import golden
+    res = _run(_orchestrator_two_ranks)
+    g = golden("config1.npz")
+    for out in res:
+        for name in ("config1_se_kg", "reifi_m52_ei"):
+            ref = g[name + "_evaluatedPoints"]
+            assert out[name].shape == ref.shape, name
+            np.testing.assert_allclose(out[name], ref, rtol=1e-9, atol=1e-12, err_msg=name)
+    assert res[0]["files"] == ["config1_se_kg_2r", "reifi_m52_ei_2r"]
