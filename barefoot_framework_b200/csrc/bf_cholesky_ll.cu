@@ -429,10 +429,10 @@ extern "C" int bf_cholesky_fused(int kern, int n, int d, int S, const double* X,
     const size_t smem = ll_smem_bytes(p.np, d);
     int rc = 0;
     switch (d) {
-#define BF_CASE(DD) case DD: rc = ll_launch<DD, true>(p, S, smem, (cudaStream_t)stream); break;
-        BF_CASE(1) BF_CASE(2) BF_CASE(3) BF_CASE(4) BF_CASE(5) BF_CASE(6) BF_CASE(7) BF_CASE(8)
-#undef BF_CASE
-        default: rc = ll_launch<0, true>(p, S, smem, (cudaStream_t)stream); break;      // nDim 9..16 at run time
+        // this kernel is an option, not the default path: one compile-time instantiation (nDim = 6, the shape all
+        // measurements quote) and the run-time-dimension form keep the build short
+        case 6: rc = ll_launch<6, true>(p, S, smem, (cudaStream_t)stream); break;
+        default: rc = ll_launch<0, true>(p, S, smem, (cudaStream_t)stream); break;
     }
     if (rc) return rc;
     BF_CHECK_LAUNCH("bf_cholesky_fused");
