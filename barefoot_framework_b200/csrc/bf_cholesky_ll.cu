@@ -300,13 +300,13 @@ __global__ void __launch_bounds__(BF_LL_THREADS, BF_LL_CTAS_PER_SM) bf_cholesky_
                 Ld[8 * t + r][8 * u + 2 * q + 1] = c[t][u][1];
             }
         __syncwarp();
-        const int b = rl_factor_block(Ld, rdiag, lane);
+        const int b = rl_factor_block_blocked(Ld, rdiag, lane);
         LL_MARK(4);
         if (b && lane == 0 && bad == 0) bad = 32 * jd + b;
 #pragma unroll 8
         for (int jj = 0; jj < 32; ++jj) A[(size_t)(32 * jd + jj) * np + 32 * jd + lane] = Ld[jj][lane];
         double (*Li)[33] = Li0 + 32 * (jd & 1);
-        rl_invert_block(Ld, rdiag, Li, lane);
+        rl_invert_block_blocked(Ld, rdiag, Li, lane);
         LL_MARK(5);
         if (p.dinv) {
             double* dv = p.dinv + ((size_t)set * nb + jd) * 1024;

@@ -231,11 +231,11 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_cholesky_rl_kernel(int n,
     // Diagonal block kb sits in Ld: factor it, write L_kk, invert it into Li (warp 0 only).
     auto factor_diag = [&](int kb) {
         const int r0 = 32 * kb;
-        const int b = rl_factor_block(Ld, rdiag, lane);
+        const int b = rl_factor_block_blocked(Ld, rdiag, lane);
         if (b && lane == 0 && bad == 0) bad = r0 + b;
 #pragma unroll 8
         for (int j = 0; j < 32; ++j) A[(size_t)(r0 + j) * np + r0 + lane] = Ld[j][lane];
-        rl_invert_block(Ld, rdiag, Li, lane);
+        rl_invert_block_blocked(Ld, rdiag, Li, lane);
         if (dinv_all) {                 // inverses of the diagonal blocks, row-major 32 x 32 each (solve path)
             double* dv = dinv_all + ((size_t)blockIdx.x * (np / 32) + kb) * 1024;
 #pragma unroll 8
