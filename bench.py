@@ -81,7 +81,9 @@ def config_dict(n_gpus):
             "hyperparameter_sets": 1, "acquisitions": ["EI", "PI", "UCB"],
             "sharding": "candidate tiles, %d rank(s); all-gather of per-rank (value, index)" % n_gpus,
             "l2": "inputs rotate through a ring of %d candidate batches (%d MB > 126 MB L2)"
-                  % (RING, RING * N_CAND * N_DIM * 8 // 10 ** 6)}
+                  % (RING, RING * N_CAND * N_DIM * 8 // 10 ** 6),
+            "pipeline": "two work items in flight: the set-up of item s+1 runs on a side stream under the sweep of item s; "
+                        "in the e2e loop its host->device copy and the read of item s-1 overlap that sweep too"}
 
 
 # ---------------------------------------------------------------------------------------------
