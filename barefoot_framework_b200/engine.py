@@ -236,7 +236,7 @@ def build_factors(kern, X, y, l_sq, sigma_f, yerr, ndim=None, set_hp=None, n_set
     alpha = torch.empty((S, n), dtype=F64, device=dev)
     info = torch.zeros((S,), dtype=torch.int32, device=dev)
     per_set = 2 * np_ * np_ * 8
-    chunk = S if keep_dense else max(1, min(S, 65535, chunk_bytes // per_set))
+    chunk = max(1, S) if keep_dense else max(1, min(S, 65535, chunk_bytes // per_set))
     Lbuf = _scratch((chunk, np_, np_), dev)
     Libuf = torch.empty((chunk, np_, np_), dtype=F64, device=dev)
     st = stream()

@@ -63,6 +63,14 @@ def checkParameterInputs(*args, **kwargs):
 # ---------------------------------------------------------------------------------------------
 # one sweep = posterior + acquisition(s) for every set
 # ---------------------------------------------------------------------------------------------
+def _ts_discard(n_sets, n_candidates):
+    """Advance the global NumPy RNG exactly as thompson_sampling would for n_sets sets it does not evaluate here
+    (one normal per candidate and set, acquisitionFunc.py:243): ranks that shard the sets keep ONE random stream -
+    every rank ends in the state a single process would have, and each set sees the draws it would have seen."""
+    for _ in range(int(n_sets)):
+        np.random.normal(size=int(n_candidates))
+
+
 def _sweep(f, scale, shift, x_test, names, stage, curr_max, iteration, xi, M=None):
     """Run the fused posterior for every set of `f` and return {name: (values [S], indices [S])}
     as host arrays, plus "max_mean" [S].  PI / UCB spread: sqrt(var) in the ROM stage
@@ -150,24 +158,28 @@ def fused_calculate_batch(model, x_fused, hp_sets, kernel, x_test, curr_max, sam
             err = e
         bdist.raise_together(err, "fused_calculate_batch")
         return _sweep_candidate_sharded(f, scale, shift, x_test, name, "TM", curr_max, iteration, xi)
-    lo, hi = bdist.shard_range(hp.shape[0]) if deterministic else (0, hp.shape[0])
+    # hyper-parameter sets are sharded over the ranks of a torchrun job; only (value, index) records travel.  The
+    # host-RNG members (TS, and TS inside Hedge) are sharded too: a rank draws for its own sets and discards the
+    # draws of the others in set order (_ts_discard), so the stream is the single-process one on every rank.
+    H_all, N_all = hp.shape[0], x_test.shape[0]
+    lo, hi = bdist.shard_range(H_all)
+    names = _HEDGE_ORDER if sampleOpt == "Hedge" else [name]
     err = r = f = None
     try:
         f, scale, shift = model.create_fused_GP_batch(x_fused, hp[lo:hi], kernel, targets=targets)
-        r = _sweep(f, scale, shift, x_test, _HEDGE_ORDER if sampleOpt == "Hedge" else [name], "TM", curr_max,
-                   iteration, xi)
+        if not deterministic:
+            _ts_discard(lo, N_all)
+        r = _sweep(f, scale, shift, x_test, names, "TM", curr_max, iteration, xi)
+        if not deterministic:
+            _ts_discard(H_all - hi, N_all)
     except Exception as e:                                     # noqa: BLE001 - re-raised on every rank below
         err = e
-    if deterministic:
-        # a set that is not positive definite (or any device error) on ONE rank must fail the stage on all
-        bdist.raise_together(err, "fused_calculate_batch")
-        # hyper-parameter sets are sharded over the ranks of a torchrun job; only (value, index) travels
-        return bdist.gather_host_sets(*r[name], n_total=hp.shape[0])
-    if err is not None:
-        raise err
+    # a set that is not positive definite (or any device error) on ONE rank must fail the stage on all
+    bdist.raise_together(err, "fused_calculate_batch")
+    g = {nm: bdist.gather_host_sets(*r[nm], n_total=H_all) for nm in names}
     if sampleOpt == "Hedge":
-        return [[[r[nm][0][h], int(r[nm][1][h])] for nm in _HEDGE_ORDER] for h in range(f.S)]
-    return r[name]
+        return [[[g[nm][0][h], int(g[nm][1][h])] for nm in _HEDGE_ORDER] for h in range(H_all)]
+    return g[name]
 
 
 def fused_calculate(param):
@@ -215,8 +227,10 @@ def rom_stage_batch(model, x_fused, hp_sets, kernel, x_test, new_mean, acq, cost
     names = _HEDGE_ORDER if hedge else [acq if acq in ("KG", "TS", "EI", "PI", "UCB") else "Greedy"]
     all_keys = [(jj, kk) for jj in jj_list for kk in kk_list]
     # under torchrun the (model, fantasy point) groups are split over the ranks (all H sets of a group stay
-    # local) and the finished rows are gathered in group order; host-RNG members (TS, Hedge) keep one stream
-    sharded = acq not in ("Hedge", "TS") and bdist.world()[1] > 1
+    # local) and the finished rows are gathered in group order; for the host-RNG members (TS, Hedge) a rank
+    # discards the draws of the groups it does not hold, in order, so that the stream stays the single-process one
+    sharded = bdist.world()[1] > 1
+    uses_rng = acq in ("Hedge", "TS")
     g_lo, g_hi = bdist.shard_range(len(all_keys)) if sharded else (0, len(all_keys))
     keys = all_keys[g_lo:g_hi]
     G = len(keys)
@@ -232,6 +246,8 @@ def rom_stage_batch(model, x_fused, hp_sets, kernel, x_test, new_mean, acq, cost
     err = None
     try:
         base_means, base_vars = model.fused_rows_device(x_fused)
+        if uses_rng:
+            _ts_discard(g_lo * H, N)
         for g0 in range(0, G, groups_per_chunk):
             chunk = keys[g0:g0 + groups_per_chunk]
             if fantasy == "refactor":
@@ -287,6 +303,8 @@ def rom_stage_batch(model, x_fused, hp_sets, kernel, x_test, new_mean, acq, cost
                 parts[nm][1].append(np.asarray(rc[nm][1], dtype=np.int64))
             parts["max_mean"].append(np.asarray(rc["max_mean"], dtype=np.float64))
             del f, Z, ZE
+        if uses_rng:
+            _ts_discard((len(all_keys) - g_hi) * H, N)
     except Exception as e:                                     # noqa: BLE001 - re-raised below on every rank
         err = e
     if sharded:
@@ -407,11 +425,9 @@ def batch_acquisition_batch(modelGP, hp_sets, x_test, curr_max, acqFunc, iterati
     x_test = np.asarray(x_test, dtype=np.float64)
     hp = np.atleast_2d(np.asarray(hp_sets, dtype=np.float64))
     H_total = hp.shape[0]
+    N_all = x_test.shape[0]
     world = bdist.world()[1]
-    by_candidates = acqFunc not in ("KG", "Hedge", "TS") and world > 1 and H_total < world <= x_test.shape[0]
-    if acqFunc not in ("KG", "Hedge", "TS") and not by_candidates:
-        lo, hi = bdist.shard_range(H_total)               # sets sharded over ranks, gathered below
-        hp = hp[lo:hi]
+    by_candidates = acqFunc not in ("KG", "Hedge", "TS") and world > 1 and H_total < world <= N_all
     x = np.asarray(modelGP.x_train, dtype=np.float64)
     x = x.reshape(x.shape[0], -1)
     y = np.asarray(modelGP.y_train, dtype=np.float64) - float(modelGP.mean)
@@ -427,7 +443,11 @@ def batch_acquisition_batch(modelGP, hp_sets, x_test, curr_max, acqFunc, iterati
         nm = acqFunc if acqFunc in ("EI", "PI", "UCB") else "Greedy"
         return _sweep_candidate_sharded(f, None if shift is None else torch.ones_like(shift), shift, x_test, nm, "BATCH",
                                         curr_max, iteration, xi)
-    sharded = acqFunc not in ("KG", "Hedge", "TS")
+    # sets sharded over the ranks and gathered below; the host-RNG members draw for their own sets and discard the
+    # other sets' draws in set order (_ts_discard)
+    lo, hi = bdist.shard_range(H_total)
+    hp = hp[lo:hi]
+    uses_rng = acqFunc in ("Hedge", "TS")
     name = acqFunc if acqFunc in ("TS", "EI", "PI", "UCB") else "Greedy"
     err = r = f = None
     try:
@@ -437,24 +457,25 @@ def batch_acquisition_batch(modelGP, hp_sets, x_test, curr_max, acqFunc, iterati
         if modelGP.mean:
             shift = torch.full((f.S,), float(modelGP.mean), dtype=engine.F64, device=f.X.device)
         scale = None if shift is None else torch.ones_like(shift)
+        if uses_rng:
+            _ts_discard(lo, N_all)
         if acqFunc in ("KG", "Hedge"):
             names = [n for n in (_HEDGE_ORDER if acqFunc == "Hedge" else ()) if n != "KG"]
             r = _sweep(f, scale, shift, x_test, names, "BATCH", curr_max, iteration, xi) if names else {}
-            r["KG"] = engine.kg_full_from_factors(f, x_test, shift=float(modelGP.mean), sn=SN_KG)
+            r["KG"] = engine.kg_full_from_factors(f, x_test, shift=float(modelGP.mean), sn=SN_KG) if f.S else \
+                (np.zeros(0), np.zeros(0, dtype=np.int64))
         else:
             r = _sweep(f, scale, shift, x_test, [name], "BATCH", curr_max, iteration, xi)
+        if uses_rng:
+            _ts_discard(H_total - hi, N_all)
     except Exception as e:                                     # noqa: BLE001 - re-raised on every rank below
         err = e
-    if sharded:
-        bdist.raise_together(err, "batch_acquisition_batch")   # before the gather: all ranks raise or none
-        return bdist.gather_host_sets(*r[name], n_total=H_total)
-    if err is not None:
-        raise err
-    if acqFunc == "KG":
-        return r["KG"]
+    bdist.raise_together(err, "batch_acquisition_batch")       # before the gather: all ranks raise or none
+    members = _HEDGE_ORDER if acqFunc == "Hedge" else (["KG"] if acqFunc == "KG" else [name])
+    g = {nm: bdist.gather_host_sets(*r[nm], n_total=H_total) for nm in members}
     if acqFunc == "Hedge":
-        return [[[r[nm][0][h], int(r[nm][1][h])] for nm in _HEDGE_ORDER] for h in range(f.S)]
-    return r[name]
+        return [[[g[nm][0][h], int(g[nm][1][h])] for nm in _HEDGE_ORDER] for h in range(H_total)]
+    return g[members[0]]
 
 
 def batch_acquisition_multi(modelGP, hp_sets, x_test, curr_max, names=("EI", "PI", "UCB"), iteration=1, xi=0.01,

@@ -331,6 +331,24 @@ def _tm_stage_candidate_sharded(rank, world):
     for opt in ("EI", "UCB"):
         v, i = util.batch_acquisition_batch(gp, b["hps"][:1], b["x_test"], float(b["curr_max"]), opt, iteration=2)
         out[("batch", opt, 0)] = (float(v[0]), int(i[0]), float(b[f"k0_{opt}_val"][0]), int(b[f"k0_{opt}_idx"][0]))
+    # dense-covariance KG of the batch-only path with the SETS sharded (all sets: an odd count over two ranks)
+    v, i = util.batch_acquisition_batch(gp, b["hps"], b["x_test"], float(b["curr_max"]), "KG", iteration=2)
+    for h in range(b["hps"].shape[0]):
+        out[("batch", "KG", h)] = (float(v[h]), int(i[h]), float(b["k0_KG_val"][h]), int(b["k0_KG_idx"][h]))
+    # Thompson sampling sharded over the sets: the same draws as a single process with the same seed
+    np.random.seed(99)
+    tv, ti = util.batch_acquisition_batch(gp, b["hps"], b["x_test"], float(b["curr_max"]), "TS", iteration=2)
+    state_after = np.random.get_state()[1][:4].tolist()
+    from barefoot_framework_b200 import engine
+    f = engine.build_factors(gp.kern, np.asarray(b["x"]).reshape(len(b["x"]), -1), np.asarray(b["y"], dtype=float),
+                             b["hps"][:, 1:], b["hps"][:, 0], 0.05, ndim=d)
+    res = engine.posterior_sweep(f, b["x_test"], want_mu=True, want_var=True)
+    np.random.seed(99)
+    mu, var = res.mu.cpu().numpy(), res.var.cpu().numpy()
+    for h in range(b["hps"].shape[0]):
+        draw = np.random.normal(loc=mu[h], scale=np.sqrt(var[h]))
+        out[("batch", "TS", h)] = (float(tv[h]), int(ti[h]), float(draw.max()), int(np.argmax(draw)))
+    out[("batch", "TS", "state")] = (0.0, int(state_after == np.random.get_state()[1][:4].tolist()), 0.0, 1)
     return out
 
 
@@ -355,7 +373,7 @@ def _orchestrator_two_ranks(rank, world):
     from barefoot_framework_b200.barefoot import barefoot
     workdir = bd.broadcast_object(tempfile.mkdtemp() if rank == 0 else None)
     out = {}
-    for name in ("config1_se_kg", "reifi_m52_ei"):
+    for name in ("config1_se_kg", "reifi_m52_ei", "reifi_hedge"):
         case = [c for c in toy_models.CASES if c[0] == name][0]
         ev, it = toy_models.run_case(barefoot, case[0] + "_2r", case[1], case[2], case[3], workdir)
         out[name] = ev
@@ -369,8 +387,8 @@ def test_orchestrator_under_two_ranks_matches_the_reference():
     res = _run(_orchestrator_two_ranks)
     g = golden("config1.npz")
     for out in res:
-        for name in ("config1_se_kg", "reifi_m52_ei"):
+        for name in ("config1_se_kg", "reifi_m52_ei", "reifi_hedge"):      # Hedge: TS draws sharded, one RNG stream
             ref = g[name + "_evaluatedPoints"]
             assert out[name].shape == ref.shape, name
             np.testing.assert_allclose(out[name], ref, rtol=1e-9, atol=1e-12, err_msg=name)
-    assert res[0]["files"] == ["config1_se_kg_2r", "reifi_m52_ei_2r"]
+    assert res[0]["files"] == ["config1_se_kg_2r", "reifi_hedge_2r", "reifi_m52_ei_2r"]
