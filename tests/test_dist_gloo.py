@@ -392,3 +392,24 @@ def test_orchestrator_under_two_ranks_matches_the_reference():
             assert out[name].shape == ref.shape, name
             np.testing.assert_allclose(out[name], ref, rtol=1e-9, atol=1e-12, err_msg=name)
     assert res[0]["files"] == ["config1_se_kg_2r", "reifi_hedge_2r", "reifi_m52_ei_2r"]
+
+
+def test_ts_discard_consumes_the_rng_exactly_like_thompson_sampling():
+    """Sharding the host-RNG acquisitions relies on this: skipping a foreign set with util._ts_discard leaves the
+    global NumPy RNG in the state thompson_sampling (acquisitionFunc.py:243) would leave it in - also for odd
+    candidate counts (the legacy generator caches every second normal)."""
+    from barefoot_framework_b200 import util
+    from barefoot_framework_b200.acquisitionFunc import thompson_sampling
+    rng = np.random.default_rng(0)
+    for N in (1, 7, 50, 333):
+        mu, sd = rng.normal(size=N), rng.uniform(0.1, 2.0, size=N)
+        np.random.seed(5)
+        for _ in range(3):
+            thompson_sampling(mu, sd)
+        a = np.random.get_state()
+        follow_a = np.random.normal(size=4)
+        np.random.seed(5)
+        util._ts_discard(3, N)
+        b = np.random.get_state()
+        follow_b = np.random.normal(size=4)
+        assert np.array_equal(a[1], b[1]) and a[2:] == b[2:] and np.array_equal(follow_a, follow_b)
