@@ -39,8 +39,9 @@ SIGNATURES = {
     "bf_posterior_solve_parts": (c_i, [c_i, c_ll]),
     "bf_gp_posterior_solve": (c_i, [c_i, c_ll, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_p, c_p,
                                     c_p, c_p, c_i, c_i, c_d, c_d, c_d, c_p, c_p, c_p]),
+    "bf_prescale_train": (c_i, [c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "bf_gp_posterior": (c_i, [c_i, c_ll, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
-                              c_p, c_p, c_i, c_i, c_d, c_d, c_d, c_p, c_p, c_p]),
+                              c_p, c_p, c_i, c_i, c_d, c_d, c_d, c_p, c_p, c_p, c_p]),
     "bf_gp_solve_rows": (c_i, [c_i, c_ll, c_i, c_i, c_p, c_p, c_p, c_d, c_p, c_p, c_p, c_p, c_p, c_p]),
     "bf_gp_cov": (c_i, [c_i, c_ll, c_ll, c_i, c_i, c_p, c_p, c_p, c_d, c_p, c_p, c_p, c_ll, c_p]),
     "bf_acq_finalize": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),

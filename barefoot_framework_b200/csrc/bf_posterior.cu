@@ -22,15 +22,29 @@
 // Phase timing (tools/dbg_skip.sh) needs a build with -DBF_PHASE_PROFILE; the shipped library has no such switch.
 #ifdef BF_PHASE_PROFILE
 #define BF_SKIP(p, bit) ((p).debug_skip & (bit))
+// cycle accounting per warp (BF_DEBUG_SKIP=64): slot 0 = wait at the loop-top barrier, 1 = phase C, 2 = phase A,
+// 3 = wait at the barrier before phase B, 4 = phase B; one CTA prints its 16 warps when it retires
+#define BF_PROF_DECL long long prof_t[5] = {0, 0, 0, 0, 0}; long long prof_c = clock64(); const long long prof_start = prof_c
+#define BF_PROF_MARK(k) do { const long long c_ = clock64(); prof_t[k] += c_ - prof_c; prof_c = c_; } while (0)
+#define BF_PROF_REPORT                                                                                              \
+    do {                                                                                                            \
+        if ((p.debug_skip & 64) && blockIdx.x == 700 && blockIdx.y == 0 && lane == 0)                               \
+            printf("prof warp %2d pairs %lld total %lld wait_top %lld C %lld A %lld wait_mid %lld B %lld\n", warp,   \
+                   (long long)cap, clock64() - prof_start, prof_t[0], prof_t[1], prof_t[2], prof_t[3], prof_t[4]); \
+    } while (0)
 #else
 #define BF_SKIP(p, bit) 0
+#define BF_PROF_DECL
+#define BF_PROF_MARK(k)
+#define BF_PROF_REPORT
 #endif
 
 struct PostParams {
     int kern, n, d, np, nb, NT, NTA, S;
     long long N;
-    const double *Xs, *X, *inv_l2, *amp, *linv, *alpha, *scale, *shift;
+    const double *Xs, *Xw, *inv_l2, *amp, *linv, *alpha, *scale, *shift;
     const int32_t* set_hp;
+    unsigned* pair_ctr;   // per-set work counters of the dual kernel (NULL: static split)
     size_t linv_stride;
     double *mu_out, *var_out;
     int acq_mask, spread_is_sqrt;
@@ -49,20 +63,21 @@ struct PostParams {
 // B-tile layout: cell ((g * NTA + a) * 32 + lane) holds k*[4g + (lane & 3)][8a + (lane >> 2)], the
 // DMMA B fragment of atom a at k-group g.  The calling warp generates k-groups g_first, g_first +
 // g_stride, ... < g_end and leaves its share of the mean in row `slot` of mpart.
-template <int D, int NTA>
-__device__ __forceinline__ void gen_tile(const PostParams& p, const double* __restrict__ w_s,
-                                         const double* __restrict__ xs_s, double* __restrict__ Bt,
-                                         double* __restrict__ mpart, const double* __restrict__ alpha,
-                                         double amp, const double* __restrict__ tab, int g_first, int g_stride,
-                                         int g_end, int slot) {
+// xw: the training inputs of this set's hyper-parameter row, pre-scaled by the metric (bf_prescale_train);
+// the candidates in xs_s are pre-scaled too, so a squared distance is one subtraction and one FMA per
+// dimension and nothing per training row.  The loop body is straight-line code (padded rows are computed
+// from the last real row and masked, not branched around), so the NTA evaluation chains of a lane interleave.
+template <int D, int NTA, int KERN>
+__device__ __forceinline__ void gen_tile_k(const PostParams& p, const double* __restrict__ xw,
+                                           const double* __restrict__ xs_s, double* __restrict__ Bt,
+                                           double* __restrict__ mpart, const double* __restrict__ alpha,
+                                           double amp, const double* __restrict__ tab, int g_first, int g_stride,
+                                           int g_end, int slot) {
     constexpr int NT = 8 * NTA;
-    constexpr int DR = D ? D : BF_MAX_DIM;   // D == 0: nDim is a run-time value (9..16)
+    constexpr int DR = D ? D : BF_MAX_DIM;   // D == 0: nDim is a run-time value
     const int dd = D ? D : p.d;
     const int lane = threadIdx.x & 31;
     const int kk = lane & 3, nn = lane >> 2;
-    double w[DR];
-#pragma unroll
-    for (int a = 0; a < DR; ++a) w[a] = a < dd ? w_s[a] : 0.0;           // metric scale (bf_metric_scale)
     const double* xc = xs_s + nn;            // this lane's candidates (pre-scaled): xc[a * NT + 8 * at]
     double macc[NTA];
 #pragma unroll
@@ -72,22 +87,30 @@ __device__ __forceinline__ void gen_tile(const PostParams& p, const double* __re
     for (int g = g_first; g < g_end; g += g_stride) {
         const int j = 4 * g + kk;
         const bool valid = j < p.n;
+        const int jc = valid ? j : p.n - 1;
+        const long long keep = valid ? -1LL : 0LL;                       // padded rows: value and weight 0
         double xj[DR];
 #pragma unroll
-        for (int a = 0; a < DR; ++a) xj[a] = (valid && a < dd) ? __ldg(p.X + (size_t)j * dd + a) * w[a] : 0.0;
-        const double aj = valid ? __ldg(alpha + j) : 0.0;
+        for (int a = 0; a < DR; ++a) xj[a] = a < dd ? __ldg(xw + (size_t)jc * dd + a) : 0.0;
+        const double aj = __longlong_as_double(__double_as_longlong(__ldg(alpha + jc)) & keep);
         double* out = Bt + (size_t)g * NTA * 32 + lane;
+        double q[NTA];
 #pragma unroll
-        for (int at = 0; at < NTA; ++at) {
-            double q = 0.0;
+        for (int at = 0; at < NTA; ++at) q[at] = 0.0;
 #pragma unroll
-            for (int a = 0; a < DR; ++a) {
-                if (a < dd) {
-                    const double df = xc[a * NT + 8 * at] - xj[a];              // both pre-scaled
-                    q = fma(df, df, q);
+        for (int a = 0; a < DR; ++a) {
+            if (a < dd) {
+#pragma unroll
+                for (int at = 0; at < NTA; ++at) {
+                    const double df = xc[a * NT + 8 * at] - xj[a];                  // both pre-scaled
+                    q[at] = fma(df, df, q[at]);
                 }
             }
-            const double val = valid ? amp * bf_radial_q(p.kern, q, tab) : 0.0;
+        }
+#pragma unroll
+        for (int at = 0; at < NTA; ++at) {
+            const double val =
+                __longlong_as_double(__double_as_longlong(amp * bf_radial_q_k<KERN>(q[at], tab)) & keep);
             macc[at] = fma(aj, val, macc[at]);
             out[at * 32] = val;
         }
@@ -100,6 +123,21 @@ __device__ __forceinline__ void gen_tile(const PostParams& p, const double* __re
         v += __shfl_xor_sync(0xffffffffu, v, 2);
         if (kk == 0) mpart[slot * NT + 8 * at + nn] = v;
     }
+}
+
+// the covariance function is a compile-time constant of the loop (one copy of the loop per function)
+template <int D, int NTA>
+__device__ __forceinline__ void gen_tile(const PostParams& p, const double* __restrict__ xw,
+                                         const double* __restrict__ xs_s, double* __restrict__ Bt,
+                                         double* __restrict__ mpart, const double* __restrict__ alpha,
+                                         double amp, const double* __restrict__ tab, int g_first, int g_stride,
+                                         int g_end, int slot) {
+    if (p.kern == BF_KERN_SE)
+        gen_tile_k<D, NTA, BF_KERN_SE>(p, xw, xs_s, Bt, mpart, alpha, amp, tab, g_first, g_stride, g_end, slot);
+    else if (p.kern == BF_KERN_M32)
+        gen_tile_k<D, NTA, BF_KERN_M32>(p, xw, xs_s, Bt, mpart, alpha, amp, tab, g_first, g_stride, g_end, slot);
+    else
+        gen_tile_k<D, NTA, BF_KERN_M52>(p, xw, xs_s, Bt, mpart, alpha, amp, tab, g_first, g_stride, g_end, slot);
 }
 
 // ---- phase B ------------------------------------------------------------------------------
@@ -252,7 +290,7 @@ __global__ void __launch_bounds__(BF_THREADS, MINB) bf_posterior_kernel(PostPara
     }
     __syncthreads();
 
-    gen_tile<D, NTA>(p, w_s, xs_s, Bt, mpart, p.alpha + (size_t)set * p.n, amp, tab_s, threadIdx.x >> 5, BF_WARPS,
+    gen_tile<D, NTA>(p, p.Xw + (size_t)hp * p.n * dd, xs_s, Bt, mpart, p.alpha + (size_t)set * p.n, amp, tab_s, threadIdx.x >> 5, BF_WARPS,
                      p.np >> 2, threadIdx.x >> 5);
     __syncthreads();
 
@@ -385,15 +423,21 @@ __global__ void __launch_bounds__(BF_DUAL_THREADS, 1) bf_posterior_dual_kernel(P
 
     const int set = blockIdx.y;
     const int hp = p.set_hp ? p.set_hp[set] : set;
-    // balanced split of the tile PAIRS over the CTAs of this set: chunk sizes differ by at most one pair,
-    // so with a CTA count that is a multiple of the SM count every SM gets the same work (no partial wave)
+    // The tile PAIRS of a set are handed out one at a time from the set's counter (p.pair_ctr, zeroed by the
+    // launcher): a CTA takes at most `cap` pairs, so an SM is released regularly (the set-up of the next work
+    // item waits for one on a high-priority stream), and every SM stays busy until the set's pairs are exhausted -
+    // the launch ends within one pair of a perfect balance whatever the block scheduler, the 17/18 split of a
+    // static partition or a concurrent kernel do.  Without a counter (p.pair_ctr == NULL) the pairs are split
+    // statically: chunk sizes differ by at most one pair.
     const long long npairs_all = (p.ntiles + 1) >> 1;
-    const long long t0 = 2 * (npairs_all * blockIdx.x / p.tiles);
-    long long t1 = 2 * (npairs_all * (blockIdx.x + 1) / p.tiles);
-    if (t1 > p.ntiles) t1 = p.ntiles;
+    const long long pr0 = npairs_all * blockIdx.x / p.tiles, pr1 = npairs_all * (blockIdx.x + 1) / p.tiles;
+    const int cap = (int)((npairs_all + p.tiles - 1) / p.tiles);
+    unsigned* ctr = p.pair_ctr ? p.pair_ctr + set : nullptr;
+    __shared__ long long s_next[2];
     const double amp = p.amp[hp];
     const double* alpha = p.alpha + (size_t)set * p.n;
     const double* Aset = p.linv + (size_t)set * p.linv_stride;
+    const double* xw = p.Xw + (size_t)hp * p.n * dd;
     const double sc = p.scale ? p.scale[set] : 1.0;
     const double sh = p.shift ? p.shift[set] : 0.0;
 
@@ -465,7 +509,7 @@ __global__ void __launch_bounds__(BF_DUAL_THREADS, 1) bf_posterior_dual_kernel(P
             const int e = gtid + k * BF_THREADS;
             const int a = e / NT, c = e - a * NT;
             const long long gi = cb + c;
-            xr[k] = (e < dd * NT && tile < t1 && gi < p.N) ? p.Xs[gi * dd + a] * w_s[a] : 0.0;   // pre-scaled
+            xr[k] = (e < dd * NT && tile < p.ntiles && gi < p.N) ? p.Xs[gi * dd + a] * w_s[a] : 0.0;   // pre-scaled
         }
     };
     auto store_xs = [&]() {
@@ -476,24 +520,48 @@ __global__ void __launch_bounds__(BF_DUAL_THREADS, 1) bf_posterior_dual_kernel(P
         }
     };
 
-    fetch_xs(t0 + grp);
+    if (threadIdx.x == 0) s_next[0] = ctr ? (long long)atomicAdd(ctr, 1u) : pr0;
+    __syncthreads();
+    long long cur = s_next[0];
+    if (!ctr && cur >= pr1) cur = npairs_all;
+    fetch_xs(2 * cur + grp);
     store_xs();
     long long prev_tile = -1;
     int buf = 0;
-    for (long long tp = t0; tp < t1; tp += 2, buf ^= 1) {
-        const long long tile = tp + grp;
-        const bool active = tile < t1;
+    BF_PROF_DECL;
+    for (int it = 0; cur < npairs_all; ++it, buf ^= 1) {
+        const long long tile = 2 * cur + grp;
+        const bool active = tile < p.ntiles;
         double* mp_cur = mpart + buf * 2 * BF_WARPS * NT;
         __syncthreads();     // candidates staged; phase B of the previous pair complete (column sums ready)
+        BF_PROF_MARK(0);
+        // thread 0 asks for the pair after this one now and publishes it before the next barrier, so the
+        // latency of the atomic hides behind phase A
+        long long grabbed = npairs_all;
+        if (threadIdx.x == 0) {
+            if (ctr) {
+                if (it + 1 < cap) grabbed = (long long)atomicAdd(ctr, 1u);
+            } else if (cur + 1 < pr1) {
+                grabbed = cur + 1;
+            }
+        }
         if (gw == 0 && prev_tile >= 0 && !BF_SKIP(p, 4)) finish_tile(prev_tile, mpart + (buf ^ 1) * 2 * BF_WARPS * NT);
-        if (active && !BF_SKIP(p, 2)) gen_tile<D, NTA>(p, w_s, xs_s, Bt, mp_cur, alpha, amp, tab_s, g_lo, 1, g_hi, gw);
+        BF_PROF_MARK(1);
+        if (active && !BF_SKIP(p, 2)) gen_tile<D, NTA>(p, xw, xs_s, Bt, mp_cur, alpha, amp, tab_s, g_lo, 1, g_hi, gw);
+        BF_PROF_MARK(2);
+        if (threadIdx.x == 0) s_next[(it + 1) & 1] = grabbed < npairs_all ? grabbed : npairs_all;
         __syncthreads();
-        fetch_xs(tile + 2);                                  // in flight during phase B
+        BF_PROF_MARK(3);
+        const long long nxt = s_next[(it + 1) & 1];
+        fetch_xs(2 * nxt + grp);                             // in flight during phase B
         if (active && !BF_SKIP(p, 1)) dual_mma<NTA>(p.nb, Aset, Bt, spart, gw);
         store_xs();
+        BF_PROF_MARK(4);
         prev_tile = active ? tile : -1;
+        cur = nxt;
     }
     __syncthreads();
+    BF_PROF_REPORT;
     if (gw == 0 && prev_tile >= 0 && !BF_SKIP(p, 4)) finish_tile(prev_tile, mpart + (buf ^ 1) * 2 * BF_WARPS * NT);
     if (!p.acq_mask) return;
     // the two finishing warps (warp 0 of each group) merge through shared memory
@@ -698,17 +766,40 @@ static int launch_posterior_tile(const PostParams& p, int dual, dim3 grid, size_
     return launch_posterior<D, 2, 1>(p, grid, smem, st);
 }
 
+// X' = X * bf_metric_scale per hyper-parameter row: the training-side operand of the cross-covariance generator
+__global__ void bf_prescale_train_kernel(int kern, long long per, int d, long long total,
+                                         const double* __restrict__ X, const double* __restrict__ inv_l2,
+                                         double* __restrict__ Xw) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const long long h = e / per, r = e - h * per;
+    Xw[e] = X[r] * bf_metric_scale(kern, inv_l2[h * d + (r % d)]);
+}
+
+extern "C" int bf_prescale_train(int kern, int n, int d, int H, const double* X, const double* inv_l2,
+                                 double* Xw, void* stream) {
+    BF_CHECK_ARG(kern >= BF_KERN_SE && kern <= BF_KERN_M52, BF_ERR_ARG, "bf_prescale_train: bad kern %d", kern);
+    BF_CHECK_ARG(n > 0 && H >= 0 && d >= 1 && d <= BF_MAX_DIM, BF_ERR_ARG, "bf_prescale_train: bad sizes n=%d d=%d H=%d", n, d, H);
+    BF_CHECK_ARG(X && inv_l2 && Xw, BF_ERR_ARG, "bf_prescale_train: null argument");
+    if (H == 0) return 0;
+    const long long per = (long long)n * d, total = per * H;
+    bf_prescale_train_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kern, per, d, total, X,
+                                                                                                 inv_l2, Xw);
+    BF_CHECK_LAUNCH("bf_prescale_train");
+    return 0;
+}
+
 extern "C" int bf_gp_posterior(int kern, long long N, int n, int d, int S, const double* Xs,
-                               const double* X, const double* inv_l2, const double* amp,
+                               const double* Xw, const double* inv_l2, const double* amp,
                                const int32_t* set_hp, const double* linv_packed, const double* alpha,
                                const double* scale, const double* shift, double* mu_out,
                                double* var_out, int acq_mask, int spread_is_sqrt, double curr_max,
                                double xi, double kt, double* part_val, long long* part_idx,
-                               void* stream) {
+                               uint32_t* pair_ctr, void* stream) {
     BF_CHECK_ARG(kern >= BF_KERN_SE && kern <= BF_KERN_M52, BF_ERR_ARG, "bf_gp_posterior: bad kern %d", kern);
     BF_CHECK_ARG(N >= 0 && n > 0 && S >= 0, BF_ERR_ARG, "bf_gp_posterior: bad sizes N=%lld n=%d S=%d", N, n, S);
     BF_CHECK_ARG(d >= 1 && d <= BF_MAX_DIM, BF_ERR_SIZE, "bf_gp_posterior: nDim %d outside 1..%d", d, BF_MAX_DIM);
-    BF_CHECK_ARG(Xs && X && inv_l2 && amp && linv_packed && alpha, BF_ERR_ARG, "bf_gp_posterior: null input");
+    BF_CHECK_ARG(Xs && Xw && inv_l2 && amp && linv_packed && alpha, BF_ERR_ARG, "bf_gp_posterior: null input");
     BF_CHECK_ARG(!acq_mask || (part_val && part_idx), BF_ERR_ARG, "bf_gp_posterior: acq_mask without partial buffers");
     BF_CHECK_ARG(((uintptr_t)linv_packed & 15) == 0, BF_ERR_ALIGN, "bf_gp_posterior: linv_packed must be 16-byte aligned");
     if (N == 0 || S == 0) return 0;
@@ -718,7 +809,7 @@ extern "C" int bf_gp_posterior(int kern, long long N, int n, int d, int S, const
     p.NT = tc.NT;
     BF_CHECK_ARG(p.NT > 0, BF_ERR_SIZE, "bf_gp_posterior: n=%d too large for the shared-memory tile", n);
     p.NTA = p.NT / 8; p.S = S; p.N = N;
-    p.Xs = Xs; p.X = X; p.inv_l2 = inv_l2; p.amp = amp; p.linv = linv_packed; p.alpha = alpha;
+    p.Xs = Xs; p.Xw = Xw; p.inv_l2 = inv_l2; p.amp = amp; p.linv = linv_packed; p.alpha = alpha;
     p.scale = scale; p.shift = shift; p.set_hp = set_hp;
     p.linv_stride = bf_linv_packed_doubles(n);
     p.mu_out = mu_out; p.var_out = var_out;
@@ -735,6 +826,14 @@ extern "C" int bf_gp_posterior(int kern, long long N, int n, int d, int S, const
     BF_CHECK_ARG(S <= 65535, BF_ERR_SIZE, "bf_gp_posterior: at most 65535 sets per call (got %d)", S);
     dim3 grid(p.tiles, S);
     cudaStream_t st = (cudaStream_t)stream;
+    p.pair_ctr = tc.dual ? pair_ctr : nullptr;
+    if (p.pair_ctr) {
+        cudaError_t e = cudaMemsetAsync(p.pair_ctr, 0, sizeof(uint32_t) * (size_t)S, st);
+        if (e != cudaSuccess) {
+            bf_set_error("bf_gp_posterior: cudaMemsetAsync(pair_ctr): %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+    }
     const size_t smem = tc.dual ? posterior_dual_smem_bytes(p.np, p.NT, d) : posterior_smem_bytes(p.np, p.NT, d);
     switch (d) {
 #define BF_CASE(DD) case DD: return launch_posterior_tile<DD>(p, tc.dual, grid, smem, st);

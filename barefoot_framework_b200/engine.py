@@ -5,6 +5,8 @@ all through the C ABI in include/barefoot_sm100.h.
 One call here covers what the reference fans out as H (or m*N*H) Python work
 items (barefoot.py:1070-1073, 1271-1283, 2001-2013).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -260,6 +262,9 @@ def build_factors(kern, X, y, l_sq, sigma_f, yerr, ndim=None, set_hp=None, n_set
     f = GPFactors(kern, X, inv_l2, amp, hp_t, linv_packed, alpha, S,
                   L=Lbuf if keep_dense else None, Linv=Libuf if keep_dense else None)
     f.info = info
+    # the sweep's training-side operand: X pre-scaled by the metric of every hyper-parameter row
+    f.Xw = torch.empty((H, n, d), dtype=F64, device=dev)
+    call("bf_prescale_train", KERN[kern], n, d, H, ptr(X), ptr(inv_l2), ptr(f.Xw), st)
     # host copies of the small per-set scalars, so per-set launches (predict_cov) never read the device back
     f.amp_host = np.atleast_1d(amplitude(sigma_f, ndim)).astype(np.float64)
     f.set_hp_host = None if set_hp is None else np.asarray(set_hp, dtype=np.int64)
@@ -288,7 +293,7 @@ def build_factors_overlapped(*args, **kwargs):
         ready = torch.cuda.Event()
         ready.record(_setup_stream)
     main.wait_event(ready)
-    for t in (f.X, f.inv_l2, f.amp, f.set_hp, f.linv_packed, f.alpha, f.info, f.L, f.Linv):
+    for t in (f.X, f.Xw, f.inv_l2, f.amp, f.set_hp, f.linv_packed, f.alpha, f.info, f.L, f.Linv):
         if t is not None:
             t.record_stream(main)
     return f
@@ -398,6 +403,8 @@ class SweepResult:
 
 # bench.py sets this to a list to receive one (start, end) CUDA-event pair per bf_gp_posterior launch
 posterior_events = None
+# True: the static split of the candidate tiles over the CTAs of a set (measurement aid; same results)
+STATIC_TILE_SPLIT = bool(int(os.environ.get("BF_STATIC_TILE_SPLIT", "0")))
 
 
 def posterior_sweep(f, Xs, scale=None, shift=None, want_mu=False, want_var=False, acq_mask=0,
@@ -437,18 +444,21 @@ def posterior_sweep(f, Xs, scale=None, shift=None, want_mu=False, want_var=False
         hp_p = None if f.set_hp is None else f.set_hp[s0:].data_ptr()
         inv_p = f.inv_l2 if f.set_hp is not None else f.inv_l2[s0:]
         amp_p = f.amp if f.set_hp is not None else f.amp[s0:]
+        xw_p = f.Xw if f.set_hp is not None else f.Xw[s0:]
+        # per-set work counters: the candidate tiles of a set go to its CTAs dynamically (cleared by the call)
+        ctr = None if STATIC_TILE_SPLIT else torch.empty((sc,), dtype=torch.int32, device=dev)
         if posterior_events is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
         with _Section("posterior_kernel"):
-            call("bf_gp_posterior", KERN[f.kern], N, f.n, f.d, sc, ptr(Xs), ptr(f.X), inv_p.data_ptr(),
+            call("bf_gp_posterior", KERN[f.kern], N, f.n, f.d, sc, ptr(Xs), xw_p.data_ptr(), inv_p.data_ptr(),
                  amp_p.data_ptr(), hp_p, f.linv_packed[s0:].data_ptr(), f.alpha[s0:].data_ptr(),
                  None if scale is None else scale[s0:].data_ptr(),
                  None if shift is None else shift[s0:].data_ptr(),
                  None if out.mu is None else out.mu[s0:].data_ptr(),
                  None if out.var is None else out.var[s0:].data_ptr(),
                  acq_mask, int(bool(spread_is_sqrt)), float(curr_max), float(xi), float(kt),
-                 ptr(pv), ptr(pi), st)
+                 ptr(pv), ptr(pi), ptr(ctr), st)
         if posterior_events is not None:
             ev1.record()
             posterior_events.append((ev0, ev1))

@@ -111,15 +111,22 @@ int bf_factor_finish_kernels(int n, int S, int with_alpha);
  * written to part_val [S x parts x 5] / part_idx [S x parts x 4], parts = bf_posterior_parts(n, N, S);
  * reduce with bf_acq_finalize(S, parts, ...).
  * spread_is_sqrt: PI/UCB receive sqrt(var') (ROM stage, util.py:451,519) instead of var'
- * (TM/batch stage, util.py:598-612).  EI always receives var' (util.py:323-326). */
+ * (TM/batch stage, util.py:598-612).  EI always receives var' (util.py:323-326).
+ * Xw [H x n x d] are the training inputs pre-scaled by the metric of every hyper-parameter row
+ * (bf_prescale_train, once per GP); Xs are the plain candidates.
+ * pair_ctr: optional scratch of S 32-bit words (any contents; cleared by the call on `stream`).  With it the
+ * candidate tiles of a set are handed to the set's CTAs dynamically (the launch ends within one tile pair of a
+ * perfect balance); NULL = static split.  Results are identical either way. */
+int bf_prescale_train(int kern, int n, int d, int H, const double* X, const double* inv_l2,
+                      double* Xw, void* stream);
 int bf_gp_posterior(int kern, long long N, int n, int d, int S,
-                    const double* Xs, const double* X,
+                    const double* Xs, const double* Xw,
                     const double* inv_l2, const double* amp, const int32_t* set_hp,
                     const double* linv_packed, const double* alpha,
                     const double* scale, const double* shift,
                     double* mu_out, double* var_out,
                     int acq_mask, int spread_is_sqrt, double curr_max, double xi, double kt,
-                    double* part_val, long long* part_idx, void* stream);
+                    double* part_val, long long* part_idx, uint32_t* pair_ctr, void* stream);
 
 /* The same posterior for FEW candidates per set (the literal ROM stage: every work item of
  * barefoot.py:1001-1073 factorises its own fused GP and evaluates only sampleCount ~ 50 candidates,

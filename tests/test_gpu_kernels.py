@@ -4,6 +4,7 @@ golden vectors of the verbatim reference.  Run on the B200 box: pytest -m gpu.
 Tolerances.  Indices / labels / medoids: bit-exact.  Posterior mean, variance and
 acquisition values: |delta| <= 1e-9 * max(|ref|, scale) where scale is the prior amplitude
 (variance, cancellation near training points - SURVEY.md 7.3) or max|ref| (mean)."""
+import os
 import warnings
 
 import numpy as np
@@ -463,7 +464,7 @@ def test_edge_sizes(eng):
     from barefoot_framework_b200 import _lib
     lib = _lib.load()
     assert lib.bf_gp_posterior(0, 0, 1, 2, 1, None, None, None, None, None, None, None, None, None, None, None,
-                               0, 0, 0.0, 0.0, 0.0, None, None, None) != 0      # null inputs are rejected ...
+                               0, 0, 0.0, 0.0, 0.0, None, None, None, None) != 0      # null inputs are rejected ...
     assert b"null input" in lib.bf_last_error()
     empty = eng.posterior_sweep(f, np.zeros((0, 2)), want_mu=True)               # ... an empty batch is a no-op
     assert empty.mu.shape == (1, 0)
@@ -744,3 +745,21 @@ def test_device_exp_accuracy_over_the_whole_range(eng):
     assert np.isfinite(got).all()
     with pytest.raises(np.linalg.LinAlgError):
         eng.build_factors("SE", x, np.zeros(n), np.array([[np.nan]]), [1.0], 0.05)
+
+
+def test_radial_forms_bit_identical(tmp_path):
+    """The branch-free device exp / sqrt of the cross-covariance generators (csrc/bf_common.cuh: range and NaN
+    tests on the integer pipe, rsqrt without the library's special-case branch) give the bits of their first forms
+    for every q >= 0: tools/check_radial.cu compares 2^26 inputs (uniform ranges, tiny values, every non-negative bit
+    pattern class, the clamp / flush edges) on the device."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.isfile(nvcc):
+        pytest.skip("nvcc not available on this box")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "check_radial")
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-fmad=false", "-o", exe,
+                    os.path.join(root, "tools", "check_radial.cu")], check=True, timeout=600)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
