@@ -41,6 +41,7 @@
 
 struct PostParams {
     int kern, n, d, np, nb, NT, NTA, S;
+    int sh, g_skip;       // np - n leading padding rows of the packed operand (bf_pack_store); whole k-groups of them
     long long N;
     const double *Xs, *Xw, *inv_l2, *amp, *linv, *alpha, *scale, *shift;
     const int32_t* set_hp;
@@ -65,8 +66,10 @@ struct PostParams {
 // g_stride, ... < g_end and leaves its share of the mean in row `slot` of mpart.
 // xw: the training inputs of this set's hyper-parameter row, pre-scaled by the metric (bf_prescale_train);
 // the candidates in xs_s are pre-scaled too, so a squared distance is one subtraction and one FMA per
-// dimension and nothing per training row.  The loop body is straight-line code (padded rows are computed
-// from the last real row and masked, not branched around), so the NTA evaluation chains of a lane interleave.
+// dimension and nothing per training row.  The loop body is straight-line code (padding rows are computed
+// from row 0 and masked, not branched around), so the NTA evaluation chains of a lane interleave.
+// The padding is in front (bf_pack_store): k-groups below p.g_skip are all padding and are never generated
+// (the callers start at p.g_skip; those rows of the B tile are zeroed once per CTA).
 template <int D, int NTA, int KERN>
 __device__ __forceinline__ void gen_tile_k(const PostParams& p, const double* __restrict__ xw,
                                            const double* __restrict__ xs_s, double* __restrict__ Bt,
@@ -85,10 +88,10 @@ __device__ __forceinline__ void gen_tile_k(const PostParams& p, const double* __
 
     // NTA independent branch-free evaluation chains per lane; the FP64 FMA pipe is the limit here
     for (int g = g_first; g < g_end; g += g_stride) {
-        const int j = 4 * g + kk;
-        const bool valid = j < p.n;
-        const int jc = valid ? j : p.n - 1;
-        const long long keep = valid ? -1LL : 0LL;                       // padded rows: value and weight 0
+        const int j = 4 * g + kk - p.sh;                                 // padded row 4g + kk is training row j
+        const bool valid = j >= 0;
+        const int jc = valid ? j : 0;
+        const long long keep = valid ? -1LL : 0LL;                       // padding rows: value and weight 0
         double xj[DR];
 #pragma unroll
         for (int a = 0; a < DR; ++a) xj[a] = a < dd ? __ldg(xw + (size_t)jc * dd + a) : 0.0;
@@ -144,9 +147,9 @@ __device__ __forceinline__ void gen_tile(const PostParams& p, const double* __re
 // One warp, one row block b, NA column atoms starting at atom a0: accumulates the column sums
 // of (L^-1[b,:] k*)^2 into cs.  The last 8 k-groups are the diagonal 32x32 block: atoms whose
 // rows lie entirely above the columns of the group are skipped.
-template <int NA, int R>
+template <int NA, int R, int SREM>
 __device__ __forceinline__ void mma_block(const double* __restrict__ Aset, const double* __restrict__ Bt,
-                                          int NTA, int a0, int b, double (&cs)[NA][2]) {
+                                          int NTA, int a0, int b, int g_skip, double (&cs)[NA][2]) {
     const int lane = threadIdx.x & 31;
     double c[4][NA][2];
 #pragma unroll
@@ -154,22 +157,59 @@ __device__ __forceinline__ void mma_block(const double* __restrict__ Aset, const
 #pragma unroll
         for (int a = 0; a < NA; ++a) c[t][a][0] = c[t][a][1] = 0.0;
 
-    const double2* Ap = reinterpret_cast<const double2*>(Aset + bf_linv_block_off(b)) + lane;
-    const double* Bp = Bt + (size_t)a0 * 32 + lane;
     const int gstride = NTA * 32;           // doubles per k-group in the B tile
-    const int ng_full = 8 * b;              // groups left of the diagonal block
+    int ng_full = 8 * b;                    // groups left of the diagonal block
+    // the first g_skip k-groups of every row are padding (zero columns of the operand): whole rounds of R
+    // groups are stepped over, the rest (s_rem groups) is left out of the first round below
+    const int skip_rounds = min(g_skip / R, ng_full / R);
+    const int s_rem = g_skip - skip_rounds * R;
+    ng_full -= skip_rounds * R;
+    const double2* Ap = reinterpret_cast<const double2*>(Aset + bf_linv_block_off(b)) + lane + (size_t)skip_rounds * R * 64;
+    const double* Bp = Bt + (size_t)a0 * 32 + lane + (size_t)skip_rounds * R * gstride;
 
     // A-operand ring: R (4 or 8) k-groups in registers; group g + R - 1 is requested while group g
     // is multiplied, so R - 1 groups (4 NA DMMAs each) cover the L2 latency.  All trip counts and
-    // ring slots are compile-time so no DMMA sits behind a run-time predicate.
+    // ring slots are compile-time so no DMMA of the main loop sits behind a run-time predicate.
     static_assert(R == 4 || R == 8, "ring depth must divide the 8 k-groups of a row block");
     double2 ring[R][2];
+    auto load_group = [&](int slot, int g) {
+        ring[slot][0] = __ldg(Ap + (size_t)g * 64);
+        ring[slot][1] = __ldg(Ap + (size_t)g * 64 + 32);
+    };
+    auto mul_group = [&](int slot, int g) {
+        double bb[NA];
 #pragma unroll
-    for (int r = 0; r < R - 1; ++r) {       // at least the 8 diagonal groups exist
-        ring[r][0] = __ldg(Ap + (size_t)r * 64);
-        ring[r][1] = __ldg(Ap + (size_t)r * 64 + 32);
+        for (int a = 0; a < NA; ++a) bb[a] = Bp[(size_t)g * gstride + a * 32];
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+            bf_dmma(c[0][a][0], c[0][a][1], ring[slot][0].x, bb[a]);
+            bf_dmma(c[1][a][0], c[1][a][1], ring[slot][0].y, bb[a]);
+            bf_dmma(c[2][a][0], c[2][a][1], ring[slot][1].x, bb[a]);
+            bf_dmma(c[3][a][0], c[3][a][1], ring[slot][1].y, bb[a]);
+        }
+    };
+    if (SREM > 0 && ng_full > 0) {
+        // first round with a compile-time number of padding groups (s_rem == SREM for every row block that
+        // has full groups): the ring starts at the first real group, nothing is loaded for the padding
+#pragma unroll
+        for (int r = 0; r < R - 1; ++r) load_group((SREM + r) % R, SREM + r);
+#pragma unroll
+        for (int r = SREM; r < R; ++r) {
+            load_group((r + R - 1) % R, r + R - 1);
+            mul_group(r, r);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R - 1; ++r) load_group(r, r);      // at least the 8 diagonal groups exist
+        if (ng_full > 0) {                  // first round; SREM < 0: groups below s_rem are padding (warp-uniform test)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                load_group((r + R - 1) % R, r + R - 1);
+                if (SREM == 0 || r >= s_rem) mul_group(r, r);
+            }
+        }
     }
-    for (int g0 = 0; g0 < ng_full; g0 += R) {           // ng_full = 8 b is a multiple of R
+    for (int g0 = R; g0 < ng_full; g0 += R) {           // ng_full is a multiple of R
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int g = g0 + r;
@@ -221,8 +261,8 @@ __device__ __forceinline__ void mma_block(const double* __restrict__ Aset, const
 // Work units = (row-block pair) x (column slice of NA atoms); warps take units round-robin.  Unit
 // u: slice = u % nslices, pair = u / nslices.  Each warp owns one slice for the whole phase so its
 // column sums stay in registers; warps beyond the unit count idle.
-template <int NA, int R>
-__device__ __forceinline__ void mma_phase_body(int nb, int NTA, const double* __restrict__ Aset,
+template <int NA, int R, int SREM>
+__device__ __forceinline__ void mma_phase_body(int nb, int NTA, int g_skip, const double* __restrict__ Aset,
                                        const double* __restrict__ Bt, double* __restrict__ spart, int warp) {
     const int lane = threadIdx.x & 31;
     const int NT = 8 * NTA;
@@ -237,8 +277,8 @@ __device__ __forceinline__ void mma_phase_body(int nb, int NTA, const double* __
     for (int a = 0; a < NA; ++a) cs[a][0] = cs[a][1] = 0.0;
     for (int pr = wq; pr < npairs; pr += nq) {
         const int b_hi = nb - 1 - pr;
-        mma_block<NA, R>(Aset, Bt, NTA, a0, b_hi, cs);
-        if (pr != b_hi) mma_block<NA, R>(Aset, Bt, NTA, a0, pr, cs);
+        mma_block<NA, R, SREM>(Aset, Bt, NTA, a0, b_hi, g_skip, cs);
+        if (pr != b_hi) mma_block<NA, R, SREM>(Aset, Bt, NTA, a0, pr, g_skip, cs);
     }
     // column c = 8 (a0 + a) + 2 (lane & 3) + q; reduce over the 8 row lanes (lane >> 2)
 #pragma unroll
@@ -255,9 +295,17 @@ __device__ __forceinline__ void mma_phase_body(int nb, int NTA, const double* __
 
 // single-buffer kernel: out-of-line copy per register budget
 template <int NA, int MINB>
-__device__ __noinline__ void mma_phase(int nb, int NTA, const double* __restrict__ Aset,
+__device__ __noinline__ void mma_phase(int nb, int NTA, int g_skip, const double* __restrict__ Aset,
                                        const double* __restrict__ Bt, double* __restrict__ spart, int warp) {
-    mma_phase_body<NA, 4>(nb, NTA, Aset, Bt, spart, warp);
+    mma_phase_body<NA, 4, -1>(nb, NTA, g_skip, Aset, Bt, spart, warp);
+}
+
+// the 24-candidate tiles of the dual kernel (n <= 544): one copy per number of leading padding groups mod 4, so
+// the first round of a row block is compile-time code like the rest (SREM < 0 above tests it at run time)
+template <int SREM>
+__device__ __noinline__ void mma_phase_3(int nb, int NTA, int g_skip, const double* __restrict__ Aset,
+                                         const double* __restrict__ Bt, double* __restrict__ spart, int warp) {
+    mma_phase_body<3, 4, SREM>(nb, NTA, g_skip, Aset, Bt, spart, warp);
 }
 
 template <int D, int NTA, int MINB>
@@ -280,6 +328,7 @@ __global__ void __launch_bounds__(BF_THREADS, MINB) bf_posterior_kernel(PostPara
     const double amp = p.amp[hp];
 
     for (int e = threadIdx.x; e < BF_WARPS * NT; e += BF_THREADS) spart[e] = 0.0;
+    for (int e = threadIdx.x; e < p.g_skip * NTA * 32; e += BF_THREADS) Bt[e] = 0.0;   // all-padding k-groups
     if (threadIdx.x < dd) w_s[threadIdx.x] = bf_metric_scale(p.kern, p.inv_l2[(size_t)hp * dd + threadIdx.x]);
     for (int e = threadIdx.x; e < BF_EXP_TAB_N; e += BF_THREADS) tab_s[e] = bf_exp_tab_g[e];
     __syncthreads();
@@ -290,7 +339,7 @@ __global__ void __launch_bounds__(BF_THREADS, MINB) bf_posterior_kernel(PostPara
     }
     __syncthreads();
 
-    gen_tile<D, NTA>(p, p.Xw + (size_t)hp * p.n * dd, xs_s, Bt, mpart, p.alpha + (size_t)set * p.n, amp, tab_s, threadIdx.x >> 5, BF_WARPS,
+    gen_tile<D, NTA>(p, p.Xw + (size_t)hp * p.n * dd, xs_s, Bt, mpart, p.alpha + (size_t)set * p.n, amp, tab_s, p.g_skip + (threadIdx.x >> 5), BF_WARPS,
                      p.np >> 2, threadIdx.x >> 5);
     __syncthreads();
 
@@ -302,10 +351,10 @@ __global__ void __launch_bounds__(BF_THREADS, MINB) bf_posterior_kernel(PostPara
         for (int cand = (MINB == 2 && NTA > 4) ? NTA / 2 : NTA; cand >= 1; --cand)   // 128-register budget
             if (NTA % cand == 0 && (cand == 1 || BF_WARPS / (NTA / cand) <= npairs)) { NA = cand; break; }
         switch (NA) {
-            case 6: if (NTA == 6 && MINB == 1) mma_phase<6, MINB>(p.nb, NTA, Aset, Bt, spart, threadIdx.x >> 5); break;
-            case 3: if (NTA % 3 == 0) mma_phase<3, MINB>(p.nb, NTA, Aset, Bt, spart, threadIdx.x >> 5); break;
-            case 2: if (NTA % 2 == 0) mma_phase<2, MINB>(p.nb, NTA, Aset, Bt, spart, threadIdx.x >> 5); break;
-            default: mma_phase<1, MINB>(p.nb, NTA, Aset, Bt, spart, threadIdx.x >> 5); break;
+            case 6: if (NTA == 6 && MINB == 1) mma_phase<6, MINB>(p.nb, NTA, p.g_skip, Aset, Bt, spart, threadIdx.x >> 5); break;
+            case 3: if (NTA % 3 == 0) mma_phase<3, MINB>(p.nb, NTA, p.g_skip, Aset, Bt, spart, threadIdx.x >> 5); break;
+            case 2: if (NTA % 2 == 0) mma_phase<2, MINB>(p.nb, NTA, p.g_skip, Aset, Bt, spart, threadIdx.x >> 5); break;
+            default: mma_phase<1, MINB>(p.nb, NTA, p.g_skip, Aset, Bt, spart, threadIdx.x >> 5); break;
         }
     }
     __syncthreads();
@@ -391,8 +440,8 @@ __global__ void __launch_bounds__(BF_THREADS, MINB) bf_posterior_kernel(PostPara
 #define BF_DUAL_THREADS (2 * BF_THREADS)
 
 template <int NTA>
-__device__ __forceinline__ void dual_mma(int nb, const double* __restrict__ Aset, const double* __restrict__ Bt,
-                                         double* __restrict__ spart, int warp) {
+__device__ __forceinline__ void dual_mma(int nb, int g_skip, const double* __restrict__ Aset,
+                                         const double* __restrict__ Bt, double* __restrict__ spart, int warp) {
     // widest column slice (a divisor of NTA, at most 3 atoms: 128-register budget) that still gives
     // every pair queue a row-block pair
     const int npairs = (nb + 1) >> 1;
@@ -400,9 +449,18 @@ __device__ __forceinline__ void dual_mma(int nb, const double* __restrict__ Aset
     for (int cand = NTA > 4 ? NTA / 2 : NTA; cand >= 1; --cand)
         if (NTA % cand == 0 && (cand == 1 || BF_WARPS / (NTA / cand) <= npairs)) { NA = cand; break; }
     switch (NA) {
-        case 3: if (NTA % 3 == 0) mma_phase<3, 2>(nb, NTA, Aset, Bt, spart, warp); break;
-        case 2: if (NTA % 2 == 0) mma_phase<2, 2>(nb, NTA, Aset, Bt, spart, warp); break;
-        default: mma_phase<1, 2>(nb, NTA, Aset, Bt, spart, warp); break;
+        case 3:
+            if (NTA % 3 == 0) {
+                switch (g_skip & 3) {
+                    case 0: mma_phase_3<0>(nb, NTA, g_skip, Aset, Bt, spart, warp); break;
+                    case 1: mma_phase_3<1>(nb, NTA, g_skip, Aset, Bt, spart, warp); break;
+                    case 2: mma_phase_3<2>(nb, NTA, g_skip, Aset, Bt, spart, warp); break;
+                    default: mma_phase_3<3>(nb, NTA, g_skip, Aset, Bt, spart, warp); break;
+                }
+            }
+            break;
+        case 2: if (NTA % 2 == 0) mma_phase<2, 2>(nb, NTA, g_skip, Aset, Bt, spart, warp); break;
+        default: mma_phase<1, 2>(nb, NTA, g_skip, Aset, Bt, spart, warp); break;
     }
 }
 
@@ -442,6 +500,7 @@ __global__ void __launch_bounds__(BF_DUAL_THREADS, 1) bf_posterior_dual_kernel(P
     const double sh = p.shift ? p.shift[set] : 0.0;
 
     for (int e = gtid; e < BF_WARPS * NT; e += BF_THREADS) spart[e] = 0.0;   // idle-queue slots stay 0
+    for (int e = gtid; e < p.g_skip * NTA * 32; e += BF_THREADS) Bt[e] = 0.0;   // all-padding k-groups: never generated
     if (threadIdx.x < dd) w_s[threadIdx.x] = bf_metric_scale(p.kern, p.inv_l2[(size_t)hp * dd + threadIdx.x]);
     for (int e = threadIdx.x; e < BF_EXP_TAB_N; e += BF_DUAL_THREADS) tab_s[e] = bf_exp_tab_g[e];
     __syncthreads();
@@ -453,7 +512,7 @@ __global__ void __launch_bounds__(BF_DUAL_THREADS, 1) bf_posterior_dual_kernel(P
 
     // k-groups of phase A per warp: contiguous ranges; warp 0 of each group also finishes the previous
     // tile (phase C) while the others generate, so it takes a smaller share
-    const int ng = p.np >> 2;
+    const int ng = (p.np >> 2) - p.g_skip;                           // k-groups that hold training rows
     int g_lo, g_hi;
     {
         const int per = ng / BF_WARPS;
@@ -467,6 +526,8 @@ __global__ void __launch_bounds__(BF_DUAL_THREADS, 1) bf_posterior_dual_kernel(P
             g_lo = w0 + (int)((long long)rest * (gw - 1) / (BF_WARPS - 1));
             g_hi = w0 + (int)((long long)rest * gw / (BF_WARPS - 1));
         }
+        g_lo += p.g_skip;
+        g_hi += p.g_skip;
     }
 
     // phase C of one tile: one lane per candidate (two rounds when the tile has 48)
@@ -554,7 +615,7 @@ __global__ void __launch_bounds__(BF_DUAL_THREADS, 1) bf_posterior_dual_kernel(P
         BF_PROF_MARK(3);
         const long long nxt = s_next[(it + 1) & 1];
         fetch_xs(2 * nxt + grp);                             // in flight during phase B
-        if (active && !BF_SKIP(p, 1)) dual_mma<NTA>(p.nb, Aset, Bt, spart, gw);
+        if (active && !BF_SKIP(p, 1)) dual_mma<NTA>(p.nb, p.g_skip, Aset, Bt, spart, gw);
         store_xs();
         BF_PROF_MARK(4);
         prev_tile = active ? tile : -1;
@@ -805,6 +866,7 @@ extern "C" int bf_gp_posterior(int kern, long long N, int n, int d, int S, const
     if (N == 0 || S == 0) return 0;
     PostParams p;
     p.kern = kern; p.n = n; p.d = d; p.np = bf_padded_n(n); p.nb = p.np / 32;
+    p.sh = p.np - n; p.g_skip = p.sh >> 2;
     const TileChoice tc = choose_tile(n);
     p.NT = tc.NT;
     BF_CHECK_ARG(p.NT > 0, BF_ERR_SIZE, "bf_gp_posterior: n=%d too large for the shared-memory tile", n);

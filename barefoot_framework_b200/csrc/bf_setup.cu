@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_factor_finish_rl_kernel(
         for (int i = 0; i < 32; ++i) {
             const double v = Lo[i][lane];
             Linv[(size_t)(r0 + i) * np + r0 + lane] = v;
-            packed[bf_linv_elem_off(r0 + i, r0 + lane)] = v;
+            bf_pack_store(packed, r0 + i, r0 + lane, v, n, np);
         }
         for (int jb = kb + 1; jb < nb; ++jb)
             for (int i = 0; i < 32; ++i) Linv[(size_t)(r0 + i) * np + 32 * jb + lane] = 0.0;
@@ -395,8 +395,8 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_factor_finish_rl_kernel(
                     const int i = 32 * I + 8 * t + (lane >> 2), j = 32 * J + 8 * u + 2 * (lane & 3);
                     const double2 v = make_double2(-c[t][u][0], -c[t][u][1]);
                     *reinterpret_cast<double2*>(Linv + (size_t)i * np + j) = v;
-                    packed[bf_linv_elem_off(i, j)] = v.x;
-                    packed[bf_linv_elem_off(i, j + 1)] = v.y;
+                    bf_pack_store(packed, i, j, v.x, n, np);
+                    bf_pack_store(packed, i, j + 1, v.y, n, np);
                 }
         }
         __syncthreads();
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(BF_RL_THREADS, 1) bf_factor_finish_rl_kernel(
 
 
 // inverses of the diagonal blocks (warp 0) and zeros right of the diagonal (the other warps): grid (nb, S)
-__global__ void __launch_bounds__(128) bf_diag_inverse_kernel(int np, const double* __restrict__ Lall,
+__global__ void __launch_bounds__(128) bf_diag_inverse_kernel(int n, int np, const double* __restrict__ Lall,
                                                               double* __restrict__ Linv_all,
                                                               double* __restrict__ packed_all, size_t packed_stride) {
     __shared__ double Lw[32][33];
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(128) bf_diag_inverse_kernel(int np, const doub
         for (int i = 0; i < 32; ++i) {
             const double v = Lo[i][lane];
             Linv[(size_t)(r0 + i) * np + r0 + lane] = v;
-            packed[bf_linv_elem_off(r0 + i, r0 + lane)] = v;
+            bf_pack_store(packed, r0 + i, r0 + lane, v, n, np);
         }
     } else {
         const int width = np - r0 - 32;                 // doubles right of the diagonal block, per row
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(128) bf_diag_inverse_kernel(int np, const doub
 }
 
 // grid (4 nb, S): CTA = (block column J, 8-column group a); warp w owns rows 8w..8w+7 of every row block
-__global__ void __launch_bounds__(128) bf_linv_cols_kernel(int np, const double* __restrict__ Lall,
+__global__ void __launch_bounds__(128) bf_linv_cols_kernel(int n, int np, const double* __restrict__ Lall,
                                                           double* __restrict__ Linv_all,
                                                           double* __restrict__ packed_all, size_t packed_stride) {
     extern __shared__ __align__(16) double cs_sm[];
@@ -541,8 +541,8 @@ __global__ void __launch_bounds__(128) bf_linv_cols_kernel(int np, const double*
             const int i = 32 * I + 8 * warp + r, j = c0 + 2 * kk;
             *reinterpret_cast<double2*>(xh + (size_t)(I - J) * 256 + (8 * warp + r) * 8 + 2 * kk) = v;
             *reinterpret_cast<double2*>(Linv + (size_t)i * np + j) = v;
-            packed[bf_linv_elem_off(i, j)] = v.x;
-            packed[bf_linv_elem_off(i, j + 1)] = v.y;
+            bf_pack_store(packed, i, j, v.x, n, np);
+            bf_pack_store(packed, i, j + 1, v.y, n, np);
             ++I;
             K = J;
         }
@@ -758,7 +758,7 @@ __global__ void __launch_bounds__(BF_THREADS) bf_factor_finish_kernel(
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             Linv[(size_t)(r0 + i) * np + r0 + lane] = x[i];
-            packed[bf_linv_elem_off(r0 + i, r0 + lane)] = x[i];
+            bf_pack_store(packed, r0 + i, r0 + lane, x[i], n, np);
         }
         // zero the blocks to the right of the diagonal in the row-major copy
         for (int jb = kb + 1; jb < nb; ++jb)
@@ -835,8 +835,8 @@ __global__ void __launch_bounds__(BF_THREADS) bf_factor_finish_kernel(
                         v.x = -c[t][u][0];
                         v.y = -c[t][u][1];
                         *reinterpret_cast<double2*>(Linv + (size_t)i * np + j) = v;
-                        packed[bf_linv_elem_off(i, j)] = v.x;
-                        packed[bf_linv_elem_off(i, j + 1)] = v.y;
+                        bf_pack_store(packed, i, j, v.x, n, np);
+                        bf_pack_store(packed, i, j + 1, v.y, n, np);
                     }
                 __syncwarp();
                 __threadfence_block();
@@ -887,6 +887,17 @@ extern "C" int bf_factor_finish(int n, int S, const double* L, const double* y, 
     BF_CHECK_ARG(!alpha || y, BF_ERR_ARG, "bf_factor_finish: alpha requested without y");
     if (S == 0) return 0;
     const int np = bf_padded_n(n);
+    if (np != n) {
+        // the packed operand holds L^-1 shifted to the END of the padded index range (bf_pack_store): the
+        // kernels write the n x n part, everything else - the leading rows and columns, the triangles above
+        // the diagonal inside the shifted diagonal blocks - must be zero
+        cudaError_t e0 = cudaMemsetAsync(linv_packed, 0, sizeof(double) * (size_t)S * bf_linv_packed_doubles(n),
+                                         (cudaStream_t)stream);
+        if (e0 != cudaSuccess) {
+            bf_set_error("bf_factor_finish: cudaMemsetAsync: %s", cudaGetErrorString(e0));
+            return (int)e0;
+        }
+    }
     if (np <= BF_SETUP_RL_MAX_NP && S <= bf_setup_cols_max_sets()) {
         // few sets: spread every inverse over 4 nb CTAs
         const size_t smem_c = linv_cols_smem_bytes(np);
@@ -901,8 +912,8 @@ extern "C" int bf_factor_finish(int n, int S, const double* L, const double* y, 
         cudaStream_t st = (cudaStream_t)stream;
         const int nb = np / 32;
         const size_t pstride = bf_linv_packed_doubles(n);
-        bf_diag_inverse_kernel<<<dim3(nb, S), 128, 0, st>>>(np, L, Linv, linv_packed, pstride);
-        bf_linv_cols_kernel<<<dim3(4 * nb, S), 128, smem_c, st>>>(np, L, Linv, linv_packed, pstride);
+        bf_diag_inverse_kernel<<<dim3(nb, S), 128, 0, st>>>(n, np, L, Linv, linv_packed, pstride);
+        bf_linv_cols_kernel<<<dim3(4 * nb, S), 128, smem_c, st>>>(n, np, L, Linv, linv_packed, pstride);
         if (alpha) bf_alpha_kernel<<<S, 32 * BF_ALPHA_WARPS, smem_a, st>>>(n, np, Linv, y, y_stride, alpha);
         BF_CHECK_LAUNCH("bf_factor_finish");
         return 0;

@@ -41,13 +41,26 @@ def make_problem(rng, n, d, N):
 
 
 def unpack_linv(packed, n):
-    """Invert the tensor-core operand layout (bf_common.cuh: bf_linv_elem_off)."""
+    """Invert the tensor-core operand layout (bf_common.cuh: bf_linv_elem_off, bf_pack_store): the n x n
+    inverse sits at the END of the padded index range, the leading np - n rows and columns and everything
+    above the diagonal are zero.  Returns the matrix in the dense layout (padding at the end, identity)."""
     np_ = (n + 31) // 32 * 32
+    sh = np_ - n
     i, j = np.tril_indices(np_)
     b, t, r, g, kk = i >> 5, (i & 31) >> 3, i & 7, j >> 2, j & 3
     off = 1024 * b * (b + 1) // 2 + ((g * 2 + (t >> 1)) * 32 + (r * 4 + kk)) * 2 + (t & 1)
-    out = np.zeros((np_, np_))
-    out[i, j] = packed[off]
+    shifted = np.zeros((np_, np_))
+    shifted[i, j] = packed[off]
+    assert not shifted[:sh].any() and not shifted[:, :sh].any()
+    # the triangles above the diagonal inside the diagonal blocks are part of the operand too
+    for bb in range(np_ // 32):
+        ii, jj = np.triu_indices(32, 1)
+        ii, jj = ii + 32 * bb, jj + 32 * bb
+        tt, rr, gg, k2 = (ii & 31) >> 3, ii & 7, jj >> 2, jj & 3
+        o2 = 1024 * bb * (bb + 1) // 2 + ((gg * 2 + (tt >> 1)) * 32 + (rr * 4 + k2)) * 2 + (tt & 1)
+        assert not packed[o2].any()
+    out = np.eye(np_)
+    out[:n, :n] = shifted[sh:, sh:]
     return out
 
 
