@@ -9,19 +9,24 @@
 #include "bf_block32.cuh"
 
 // ---- K = amp k(X, X) + diag(yerr_eff^2) ------------------------------------------------------
+// The covariance function and (for the common dimensions) nDim are compile-time constants: the distance
+// loop unrolls and the four elements of a thread are straight-line code that the scheduler interleaves
+// (D == 0: run-time nDim).
+template <int KERN, int D>
 __global__ void __launch_bounds__(256) bf_kernel_matrix_kernel(
-    int kern, int n, int d, int np, const double* __restrict__ X, const double* __restrict__ inv_l2,
+    int n, int d_rt, int np, const double* __restrict__ X, const double* __restrict__ inv_l2,
     const double* __restrict__ amp, const int32_t* __restrict__ set_hp, const double* __restrict__ yerr,
     int yerr_n, long long yerr_stride, double* __restrict__ K, int lower_only) {
     if (lower_only && blockIdx.x > blockIdx.y) return;      // the factorisation never reads the blocks above the diagonal
     __shared__ double xi_s[32][BF_MAX_DIM + 1];
     __shared__ double xj_s[32][BF_MAX_DIM + 1];
     __shared__ double w_s[BF_MAX_DIM];
+    const int d = D ? D : d_rt;
     const int set = blockIdx.z;
     const int hp = set_hp ? set_hp[set] : set;
     const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    if (threadIdx.x < d) w_s[threadIdx.x] = bf_metric_scale(kern, inv_l2[(size_t)hp * d + threadIdx.x]);
+    if (threadIdx.x < d) w_s[threadIdx.x] = bf_metric_scale(KERN, inv_l2[(size_t)hp * d + threadIdx.x]);
     __syncthreads();
     for (int e = threadIdx.x; e < 32 * d; e += 256) {       // pre-scaled coordinates
         const int r = e / d, a = e - r * d;
@@ -31,26 +36,38 @@ __global__ void __launch_bounds__(256) bf_kernel_matrix_kernel(
     __syncthreads();
     const double am = amp[hp];
     double* Kset = K + (size_t)set * np * np;
+    const int j = j0 + tx;
+    double q[4] = {0.0, 0.0, 0.0, 0.0};
+    if (D) {
+#pragma unroll
+        for (int a = 0; a < (D ? D : 1); ++a) {
+            const double xj = xj_s[tx][a];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const double df = xi_s[ty + 8 * rr][a] - xj;
+                q[rr] = fma(df, df, q[rr]);
+            }
+        }
+    } else {
+        for (int a = 0; a < d; ++a) {
+            const double xj = xj_s[tx][a];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const double df = xi_s[ty + 8 * rr][a] - xj;
+                q[rr] = fma(df, df, q[rr]);
+            }
+        }
+    }
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
-        const int r = ty + 8 * rr;
-        const int i = i0 + r, j = j0 + tx;
-        double v;
-        if (i < n && j < n) {
-            double q = 0.0;
-            for (int a = 0; a < d; ++a) {
-                const double df = xi_s[r][a] - xj_s[tx][a];
-                q = fma(df, df, q);
-            }
-            v = am * bf_radial_q(kern, q, bf_exp_tab_g);
-            if (i == j) {
-                const double e = yerr_n == 1 ? yerr[0] : yerr[(size_t)set * yerr_stride + i];
-                const double s = sqrt(e * e + BF_TINY);   // george folds the jitter into yerr
-                v += s * s;
-            }
-        } else {
-            v = (i == j) ? 1.0 : 0.0;
+        const int i = i0 + ty + 8 * rr;
+        double v = am * bf_radial_q_k<KERN>(q[rr], bf_exp_tab_g);      // padded rows: q = 0, overwritten below
+        if (i == j && i < n) {
+            const double e = yerr_n == 1 ? yerr[0] : yerr[(size_t)set * yerr_stride + i];
+            const double s = sqrt(e * e + BF_TINY);   // george folds the jitter into yerr
+            v += s * s;
         }
+        if (i >= n || j >= n) v = (i == j) ? 1.0 : 0.0;
         Kset[(size_t)i * np + j] = v;
     }
 }
@@ -82,8 +99,25 @@ static int kernel_matrix(int kern, int n, int d, int S, const double* X, const d
     if (S == 0) return 0;
     const int np = bf_padded_n(n);
     dim3 grid(np / 32, np / 32, S);
-    bf_kernel_matrix_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(kern, n, d, np, X, inv_l2, amp, set_hp,
-                                                                    yerr, yerr_n, yerr_stride, K, lower_only);
+    cudaStream_t st = (cudaStream_t)stream;
+#define BF_KM_LAUNCH(KK, DD)                                                                                   \
+    bf_kernel_matrix_kernel<KK, DD><<<grid, 256, 0, st>>>(n, d, np, X, inv_l2, amp, set_hp, yerr, yerr_n,       \
+                                                          yerr_stride, K, lower_only)
+#define BF_KM_DIM(KK)                                  \
+    switch (d) {                                       \
+        case 2: BF_KM_LAUNCH(KK, 2); break;            \
+        case 3: BF_KM_LAUNCH(KK, 3); break;            \
+        case 4: BF_KM_LAUNCH(KK, 4); break;            \
+        case 6: BF_KM_LAUNCH(KK, 6); break;            \
+        case 8: BF_KM_LAUNCH(KK, 8); break;            \
+        case 10: BF_KM_LAUNCH(KK, 10); break;          \
+        default: BF_KM_LAUNCH(KK, 0); break;           \
+    }
+    if (kern == BF_KERN_SE) { BF_KM_DIM(BF_KERN_SE) }
+    else if (kern == BF_KERN_M32) { BF_KM_DIM(BF_KERN_M32) }
+    else { BF_KM_DIM(BF_KERN_M52) }
+#undef BF_KM_DIM
+#undef BF_KM_LAUNCH
     BF_CHECK_LAUNCH("bf_kernel_matrix");
     return 0;
 }

@@ -224,6 +224,25 @@ def test_posterior_mean_variance(eng, kern, n, d, N):
         assert np.abs(var[h] - vref).max() <= REL * amp
 
 
+@pytest.mark.parametrize("n0,np_", [(97, 128), (225, 256)])
+def test_posterior_every_front_padding(eng, n0, np_):
+    """The packed operand is padded in front and the sweep steps over the zero k-groups (bf_pack_store): every
+    padding width 0..31 - whole and partial k-groups, every first-round specialisation, one and two skipped
+    rounds - against the oracle, with the acquisitions on so the dynamic tile hand-out runs too."""
+    for n in range(n0, np_ + 1):
+        rng = np.random.default_rng(n)
+        X, y, Xs = make_problem(rng, n, 2, 61)
+        l = rng.uniform(0.2, 0.9, size=(1, 2))
+        f = eng.build_factors("M52", X, y, l ** 2, [1.3], 0.05)
+        assert np.array_equal(unpack_linv(f.linv_packed.cpu().numpy()[0], n)[:n, :n] != 0, np.tril(np.ones((n, n))) != 0)
+        res = eng.posterior_sweep(f, Xs, want_mu=True, want_var=True, acq_mask=15, curr_max=0.2, kt=0.4)
+        g = fast.GP(X, y, l[0], 1.3, 0.05, 2, "M52")
+        mref, vref = g.predict_var(Xs)
+        assert np.abs(res.mu[0].cpu().numpy() - mref).max() <= REL * max(1.0, np.abs(mref).max()), n
+        assert np.abs(res.var[0].cpu().numpy() - vref).max() <= REL * 1.3 / 2, n
+        assert int(res.best_idx[0, 3]) == int(np.argmax(mref)), n
+
+
 def test_posterior_golden_reference_gp(eng):
     """gp_model of the verbatim reference (gpModel.py on the george restatement)."""
     g = golden("gp.npz")
