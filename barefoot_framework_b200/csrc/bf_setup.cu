@@ -911,8 +911,22 @@ static int bf_setup_cols_max_sets() {
 
 extern "C" int bf_factor_finish_kernels(int n, int S, int with_alpha) {
     const int np = bf_padded_n(n);
-    if (np <= BF_SETUP_RL_MAX_NP && S <= bf_setup_cols_max_sets()) return with_alpha ? 3 : 2;
-    return 1;
+    const int clear = np != n ? 1 : 0;                  // bf_packed_clear_kernel
+    if (np <= BF_SETUP_RL_MAX_NP && S <= bf_setup_cols_max_sets()) return clear + (with_alpha ? 3 : 2);
+    return clear + 1;
+}
+
+// Zero the cells of the packed operand that the shifted writes of the inverse never reach: in every row block
+// the 8 k-groups of its diagonal block (the n x n part is written over them afterwards) and the leading k-groups
+// that hold padding columns.  Grid (nb, S).
+__global__ void __launch_bounds__(256) bf_packed_clear_kernel(int lead_groups, double* __restrict__ packed_all,
+                                                             size_t packed_stride) {
+    const int b = blockIdx.x;
+    double* blk = packed_all + (size_t)blockIdx.y * packed_stride + bf_linv_block_off(b);
+    const int lead = lead_groups < 8 * b ? lead_groups : 8 * b;     // row block 0 is all diagonal block
+    for (int e = threadIdx.x; e < lead * 128; e += 256) blk[e] = 0.0;
+    double* diag = blk + (size_t)8 * b * 128;
+    for (int e = threadIdx.x; e < 1024; e += 256) diag[e] = 0.0;
 }
 
 extern "C" int bf_factor_finish(int n, int S, const double* L, const double* y, long long y_stride,
@@ -923,14 +937,11 @@ extern "C" int bf_factor_finish(int n, int S, const double* L, const double* y, 
     const int np = bf_padded_n(n);
     if (np != n) {
         // the packed operand holds L^-1 shifted to the END of the padded index range (bf_pack_store): the
-        // kernels write the n x n part, everything else - the leading rows and columns, the triangles above
-        // the diagonal inside the shifted diagonal blocks - must be zero
-        cudaError_t e0 = cudaMemsetAsync(linv_packed, 0, sizeof(double) * (size_t)S * bf_linv_packed_doubles(n),
-                                         (cudaStream_t)stream);
-        if (e0 != cudaSuccess) {
-            bf_set_error("bf_factor_finish: cudaMemsetAsync: %s", cudaGetErrorString(e0));
-            return (int)e0;
-        }
+        // kernels below write the n x n part; what they never touch - the leading rows and columns, the
+        // triangles above the diagonal inside the shifted diagonal blocks - is cleared first
+        bf_packed_clear_kernel<<<dim3(np / 32, S), 256, 0, (cudaStream_t)stream>>>(
+            (np - n + 3) / 4, linv_packed, bf_linv_packed_doubles(n));
+        BF_CHECK_LAUNCH("bf_factor_finish");
     }
     if (np <= BF_SETUP_RL_MAX_NP && S <= bf_setup_cols_max_sets()) {
         // few sets: spread every inverse over 4 nb CTAs

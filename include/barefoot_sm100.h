@@ -100,7 +100,10 @@ int bf_cholesky_batched_dinv(int n, int S, double* K_inout_L, int32_t* info, dou
 int bf_factor_finish(int n, int S, const double* L, const double* y, long long y_stride,
                      double* Linv, double* linv_packed, double* alpha, void* stream);
 /* Kernels one bf_factor_finish call launches: 1 (one CTA per set) or, for a few sets, 3 (diagonal
- * block inverses; column groups of L^-1 spread over 4 np/32 CTAs per set; alpha). */
+ * block inverses; column groups of L^-1 spread over 4 np/32 CTAs per set; alpha), plus one that clears the
+ * padding cells of the packed operand when n is not a multiple of 32.
+ * linv_packed is the operand of bf_gp_posterior: the n x n inverse at the END of the padded index range
+ * (element (i, j) at padded position (i + np - n, j + np - n)), zero in front. */
 int bf_factor_finish_kernels(int n, int S, int with_alpha);
 
 /* ---- (1)+(2)+(4) posterior + elementwise acquisitions: gpModel.py:50-54,
