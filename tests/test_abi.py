@@ -21,6 +21,33 @@ def test_header_and_binding_agree():
     assert sorted(_lib.SIGNATURES) == names
 
 
+def header_arg_counts():
+    """name -> number of parameters of every prototype in the header."""
+    src = open(os.path.join(ROOT, "include", "barefoot_sm100.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for name, args in re.findall(r"\b(bf_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        args = args.strip()
+        out[name] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def test_binding_and_integration_stub_have_the_header_arity():
+    """Every ctypes signature has as many arguments as its prototype, and the stub INTEGRATION.md shows a
+    reference maintainer binds the sweep and the training-side pre-scaling with the same argument lists."""
+    import ast
+    from barefoot_framework_b200 import _lib
+    counts = header_arg_counts()
+    for name, (_, args) in _lib.SIGNATURES.items():
+        assert counts[name] == len(args), (name, counts[name], len(args))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for name in ("bf_gp_posterior", "bf_prescale_train"):
+        m = re.search(r"lib\.%s\.argtypes = (\[[^\]]*\])" % name, doc)
+        assert m, name
+        listed = len(ast.parse(m.group(1), mode="eval").body.elts)
+        assert listed == counts[name], (name, listed, counts[name])
+
+
 def test_library_exports_every_symbol():
     from barefoot_framework_b200 import _lib
     if not os.path.isfile(_lib.LIB_PATH):
