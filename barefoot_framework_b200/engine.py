@@ -179,6 +179,22 @@ def _use_fused(n, d, S):
     return CHOLESKY == "ll" and bool(_lib.load().bf_cholesky_fused_supported(int(n), int(d)))
 
 
+_sm_count = None
+
+
+def _whole_waves(chunk, S):
+    """Sets per chunk of a chunked set-up: the batched Cholesky, inverse and solve kernels run one CTA (or a
+    fixed number of CTAs) per set with one CTA per SM, so a memory-limited chunk of, say, 963 sets costs
+    SEVEN waves of 148 - rounded down to a multiple of the SM count every chunk but the last fills its waves
+    (888 sets: six)."""
+    global _sm_count
+    if chunk >= S:
+        return chunk
+    if _sm_count is None:
+        _sm_count = torch.cuda.get_device_properties(device()).multi_processor_count
+    return chunk // _sm_count * _sm_count if chunk >= _sm_count else chunk
+
+
 class GPFactors:
     """Factorised GPs sharing the training inputs X: one "set" per hyper-parameter
     set (and, in the ROM stage, per fantasy point)."""
@@ -238,7 +254,7 @@ def build_factors(kern, X, y, l_sq, sigma_f, yerr, ndim=None, set_hp=None, n_set
     alpha = torch.empty((S, n), dtype=F64, device=dev)
     info = torch.zeros((S,), dtype=torch.int32, device=dev)
     per_set = 2 * np_ * np_ * 8
-    chunk = max(1, S) if keep_dense else max(1, min(S, 65535, chunk_bytes // per_set))
+    chunk = max(1, S) if keep_dense else _whole_waves(max(1, min(S, 65535, chunk_bytes // per_set)), S)
     Lbuf = _scratch((chunk, np_, np_), dev)
     Libuf = torch.empty((chunk, np_, np_), dtype=F64, device=dev)
     st = stream()
@@ -355,7 +371,7 @@ def solve_sweep(f, Xs, scale=None, shift=None, want_mu=False, want_var=False, ac
     nb = np_ // 32
     parts = lib.bf_posterior_solve_parts(n, N)
     per_set = 8 * (np_ * np_ + nb * 1024)
-    chunk = max(1, min(S, 65535, f.chunk_bytes // per_set))
+    chunk = _whole_waves(max(1, min(S, 65535, f.chunk_bytes // per_set)), S)
     Lbuf = _scratch((chunk, np_, np_), dev)
     dinv = torch.empty((chunk, nb, 32, 32), dtype=F64, device=dev)
     info = torch.zeros((S,), dtype=torch.int32, device=dev)
