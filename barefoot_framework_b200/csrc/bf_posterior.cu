@@ -456,7 +456,8 @@ __global__ void __launch_bounds__(BF_THREADS, MINB) bf_posterior_kernel(PostPara
 // and one shared-memory buffer, and all 16 warps move through phase A, phase B and phase C in
 // lock step.  Phase A then runs at the full FP64 rate with 16 warps of branch-free evaluation
 // chains, and phase B has 4 DMMA warps per scheduler to cover the L2 latency of the L^-1 stream.
-// A CTA walks a chunk of consecutive tile pairs and keeps its running maxima in registers.
+// A CTA takes tile pairs of its set one at a time from the set's work counter (or walks a static chunk of
+// consecutive pairs when the caller passes no counters) and keeps its running maxima in registers.
 #define BF_DUAL_THREADS (2 * BF_THREADS)
 
 template <int NTA>
@@ -765,8 +766,8 @@ static TileChoice choose_tile(int n) {
 
 extern "C" int bf_posterior_tile(int n) { return choose_tile(n).NT; }
 
-// Partial-result slots (= CTAs) per set.  The dual-tile kernel gives each CTA a chunk of
-// consecutive tiles: about 8 CTAs per SM over the whole launch, at least 8 tiles per chunk.
+// Partial-result slots (= CTAs) per set.  A CTA of the dual-tile kernel processes at most ceil(pairs / CTAs)
+// tile pairs of its set: about 8 CTAs per SM over the whole launch, at least 8 tiles per CTA.
 static void posterior_chunks(int n, long long N, int S, long long* ntiles, int* tpc, int* parts) {
     const TileChoice tc = choose_tile(n);
     *ntiles = 0; *tpc = 1; *parts = 0;
