@@ -39,6 +39,9 @@
 #define BF_PROF_REPORT
 #endif
 
+struct BfTrue { static constexpr bool value = true; };
+struct BfFalse { static constexpr bool value = false; };
+
 struct PostParams {
     int kern, n, d, np, nb, NT, NTA, S;
     int sh, g_skip;       // np - n leading padding rows of the packed operand (bf_pack_store); whole k-groups of them
@@ -94,23 +97,19 @@ __device__ __forceinline__ void gen_tile_k(const PostParams& p, const double* __
         for (int a = 0; a < DR; ++a) xj[a] = a < dd ? __ldg(xw + (size_t)jc * dd + a) : 0.0;
         aj0 = __ldg(alpha + jc);
     };
-    // NTA independent branch-free evaluation chains per lane; the FP64 FMA pipe is the limit here.  The row
-    // of the next k-group is requested one iteration ahead: phase B streams 1 MB through L1 between two
-    // generator phases, so these loads come from L2 (measured: 0.3-0.5 % of the launch)
-    double xn[DR], an;
-    if (g_first < g_end) load_row(g_first, xn, an);
-    for (int g = g_first; g < g_end; g += g_stride) {
+    // NTA independent branch-free evaluation chains per lane.  With the padding in front only ONE k-group can
+    // hold padding rows - group g_skip, when np - n is not a multiple of 4 - so only that step carries the row
+    // masks (MASKED); every other step is the bare evaluation (the loop is as much issue-bound as FP64-bound).
+    // (Requesting the next row one iteration ahead was measured at +0.3-0.5 % but costs 14 registers, which
+    // this form spills - not kept.)
+    int g = g_first;
+    auto step = [&](auto masked) {
+        constexpr bool MASKED = decltype(masked)::value;
         const int j = 4 * g + kk - p.sh;                                 // padded row 4g + kk is training row j
-        const bool valid = j >= 0;
-        const long long keep = valid ? -1LL : 0LL;                       // padding rows: value and weight 0
-        double xj[DR];
-#pragma unroll
-        for (int a = 0; a < DR; ++a) xj[a] = xn[a];
-        const double aj = __longlong_as_double(__double_as_longlong(an) & keep);
-        {
-            const int gn = g + g_stride < g_end ? g + g_stride : g;      // last iteration: a harmless reload
-            load_row(gn, xn, an);
-        }
+        const long long keep = (!MASKED || j >= 0) ? -1LL : 0LL;         // padding rows: value and weight 0
+        double xj[DR], a0;
+        load_row(g, xj, a0);
+        const double aj = MASKED ? __longlong_as_double(__double_as_longlong(a0) & keep) : a0;
         double* out = Bt + (size_t)g * NTA * 32 + lane;
         double q[NTA];
 #pragma unroll
@@ -127,12 +126,17 @@ __device__ __forceinline__ void gen_tile_k(const PostParams& p, const double* __
         }
 #pragma unroll
         for (int at = 0; at < NTA; ++at) {
-            const double val =
-                __longlong_as_double(__double_as_longlong(amp * bf_radial_q_k<KERN>(q[at], tab)) & keep);
+            const double v = amp * bf_radial_q_k<KERN>(q[at], tab);
+            const double val = MASKED ? __longlong_as_double(__double_as_longlong(v) & keep) : v;
             macc[at] = fma(aj, val, macc[at]);
             out[at * 32] = val;
         }
+    };
+    if (g < g_end && g == p.g_skip && (p.sh & 3)) {
+        step(BfTrue{});
+        g += g_stride;
     }
+    for (; g < g_end; g += g_stride) step(BfFalse{});
     // mean partials: sum over the 4 kk lanes, then one slot per warp (fixed-order sum later)
 #pragma unroll
     for (int at = 0; at < NTA; ++at) {
