@@ -87,3 +87,21 @@ def test_product_never_imports_oracle():
             if fn.endswith(".py"):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_set_chunks_fill_whole_waves():
+    """engine._whole_waves: a memory-limited chunk of a chunked set-up is rounded down to a multiple of the SM
+    count (the batched Cholesky / inverse / solve kernels run one CTA per set and SM), unless it already holds
+    every set or is smaller than one wave."""
+    from barefoot_framework_b200 import engine
+    saved = engine._sm_count
+    engine._sm_count = 148                       # B200; no device query on the CPU
+    try:
+        assert engine._whole_waves(963, 150000) == 888
+        assert engine._whole_waves(476, 1000) == 444
+        assert engine._whole_waves(148, 1000) == 148
+        assert engine._whole_waves(100, 1000) == 100          # less than one wave: left alone
+        assert engine._whole_waves(963, 963) == 963           # one chunk holds every set
+        assert engine._whole_waves(963, 500) == 963
+    finally:
+        engine._sm_count = saved
