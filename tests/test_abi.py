@@ -105,3 +105,26 @@ def test_set_chunks_fill_whole_waves():
         assert engine._whole_waves(963, 500) == 963
     finally:
         engine._sm_count = saved
+
+
+def test_packed_operand_cells_are_all_written_or_cleared():
+    """The packed L^-1 operand is allocated uninitialised.  bf_factor_finish must leave no cell of it undefined
+    that the sweep can read: the inverse kernels write the n x n part shifted by np - n (bf_pack_store: natural
+    lower block triangle incl. the full natural diagonal blocks), bf_packed_clear_kernel zeroes the shifted
+    diagonal blocks and the leading ceil((np - n) / 4) k-groups of every later row block first.  This restates
+    those index rules and checks that together they cover every cell of the block-lower-triangular storage."""
+    import numpy as np
+    for n in list(range(1, 200)) + [333, 480, 497, 500, 511, 512, 513, 543, 544, 700]:
+        np_ = (n + 31) // 32 * 32
+        sh, nb = np_ - n, np_ // 32
+        cover = np.zeros((np_, np_), dtype=bool)
+        lead = (sh + 3) // 4
+        for b in range(nb):
+            cover[32 * b:32 * b + 32, :4 * min(lead, 8 * b)] = True
+            cover[32 * b:32 * b + 32, 32 * b:32 * b + 32] = True
+        i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+        m = (j // 32) <= (i // 32)
+        cover[i[m] + sh, j[m] + sh] = True
+        ip, jp = np.meshgrid(np.arange(np_), np.arange(np_), indexing="ij")
+        stored = jp < 32 * (ip // 32 + 1)
+        assert (cover | ~stored).all(), n
